@@ -1,0 +1,204 @@
+"""Sector compiler: Scenario -> flat arrays + derived constants + the exact MVA lookup grid, i.e. the host-side,
+one-off part of the reference's AtcGym.__init__ (atc_gym.py:49-58, 88-110) and Corridor.__init__
+(model.py:155-186).  Everything the kernels need is plain numpy here and is copied to the device by atc_create().
+
+The MVA grid is an *exact* accelerator of Airspace.find_mva (model.py:282-292): a cell that no
+polygon edge comes within `margin` of has one answer for all of its points, which is stored; any other cell stores
+the set of polygons that could contain one of its points, and the kernel runs the reference's first-match
+bbox + ray-cast scan over just that set.
+"""
+import math
+
+import numpy as np
+
+OBS_DIM = 10
+MAX_MVA = 31
+
+
+def ray_tracing_np(x, y, ring):
+    """Vectorised restatement of model.py:318-337 for a closed ring (host side, used for the grid and faf_mva)."""
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64)
+    inside = np.zeros(x.shape, bool)
+    n = len(ring)
+    for i in range(1, n):
+        p1x, p1y = ring[i - 1]
+        p2x, p2y = ring[i]
+        if p1y == p2y:
+            continue        # y > min and y <= max cannot both hold
+        cond = (y > min(p1y, p2y)) & (y <= max(p1y, p2y)) & (x <= max(p1x, p2x))
+        xints = (y - p1y) * (p2x - p1x) / (p2y - p1y) + p1x
+        inside ^= cond & ((p1x == p2x) | (x <= xints))
+    return inside
+
+
+def _rot_apply(phi_deg, vx, vy):
+    """rot_matrix(phi) . [vx, vy]^T (model.py:345-348)"""
+    phi = math.radians(phi_deg)
+    c, s = math.cos(phi), math.sin(phi)
+    return c * vx + s * vy, -s * vx + c * vy
+
+
+class CompiledSector(object):
+    def __init__(self, scenario, cell=0.25, margin=1e-6, wind=None):
+        mvas = scenario.mvas
+        if len(mvas) > MAX_MVA:
+            raise ValueError("at most %d MVA polygons are supported" % MAX_MVA)
+        self.name = getattr(scenario, 'name', type(scenario).__name__)
+        self.rings = [np.asarray(m.area_as_list, np.float64) for m in mvas]
+        self.ring_xy = np.ascontiguousarray(np.concatenate(self.rings, 0))
+        self.ring_off = np.cumsum([0] + [len(r) for r in self.rings]).astype(np.int32)
+        self.mva_height = np.asarray([float(m.height) for m in mvas], np.float64)
+        self.mva_bounds = np.ascontiguousarray(
+            [[r[:, 0].min(), r[:, 1].min(), r[:, 0].max(), r[:, 1].max()] for r in self.rings], np.float64)
+        b = self.mva_bounds
+        self.bbox = np.asarray([b[:, 0].min(), b[:, 1].min(), b[:, 2].max(), b[:, 3].max()], np.float64)
+
+        # ---- runway / corridor (model.py:155-186, 234-246)
+        rw = scenario.runway
+        self.runway = (float(rw.x), float(rw.y), float(rw.h))
+        phi_from = rw.phi_from_runway
+        self.phi_to_runway = float((phi_from + 180) % 360)
+        self.normal = _rot_apply(phi_from, 0.0, 1.0)
+        faf_dist, faf_angle, iaf_dist = 7.4, 45, 3
+        corner_dist = iaf_dist / math.cos(math.radians(faf_angle))
+        d = _rot_apply(phi_from, 0.0, faf_dist)
+        self.faf = (rw.x + d[0], rw.y + d[1])
+        inner = _rot_apply(phi_from, 0.0, corner_dist)
+        c1 = _rot_apply(faf_angle, inner[0], inner[1])
+        c2 = _rot_apply(-faf_angle, inner[0], inner[1])
+        self.corner1 = (c1[0] + self.faf[0], c1[1] + self.faf[1])
+        self.corner2 = (c2[0] + self.faf[0], c2[1] + self.faf[1])
+        d = _rot_apply(phi_from, 0.0, faf_dist + iaf_dist)
+        self.iaf = (rw.x + d[0], rw.y + d[1])
+        self.tri_h = np.asarray([self.faf, self.corner1, self.corner2, self.faf], np.float64)
+        self.tri_1 = np.asarray([self.faf, self.corner1, self.iaf, self.faf], np.float64)
+        self.tri_2 = np.asarray([self.faf, self.corner2, self.iaf, self.faf], np.float64)
+        self.sin_to_runway, self.cos_to_runway = _rot_apply(self.phi_to_runway, 0.0, 1.0)
+        self.glide_tan = math.tan(3 * math.pi / 180)
+
+        # ---- AtcGym.__init__ constants (atc_gym.py:49-58, 88-110)
+        m = self.find_mva_np(np.asarray([self.faf[0]]), np.asarray([self.faf[1]]))[0]
+        if m < 0:
+            raise ValueError("the final approach fix lies outside the airspace")   # reference: ValueError too
+        self.faf_mva = float(self.mva_height[m])
+        lx, ly = self.bbox[2] - self.bbox[0], self.bbox[3] - self.bbox[1]
+        self.world_max_distance = float(np.hypot(lx, ly))
+        self.norm_min = np.asarray([self.bbox[0], self.bbox[1], 0, 0, 100, 0, 0, 0, -180, -180], np.float32)
+        self.norm_max = np.asarray([lx, ly, 38000, 360, 200, 38000, 38000, self.world_max_distance, 360, 360],
+                                   np.float32)
+
+        # ---- entry points (scenarios.py:192-207)
+        eps = scenario.entrypoints
+        if len(eps) > 32:
+            raise ValueError("at most 32 entry points are supported")
+        self.entry_xyphi = np.ascontiguousarray([[e.x, e.y, e.phi] for e in eps], np.float64)
+        self.level_off = np.cumsum([0] + [len(e.levels) for e in eps]).astype(np.int32)
+        self.levels = np.concatenate([np.asarray(e.levels, np.int32) for e in eps]).astype(np.int32)
+        for e in eps:
+            for lv in e.levels:
+                if not 0 <= lv * 100 <= 38000:
+                    raise ValueError("invalid altitude")            # Airplane.__init__, model.py:35-36
+
+        # ---- wind (extension)
+        self.wind = None
+        if wind is not None:
+            w = np.ascontiguousarray(wind, np.float32)
+            if w.ndim != 3 or w.shape[2] != 2 or w.shape[0] < 2 or w.shape[1] < 2:
+                raise ValueError("wind must have shape [gy >= 2, gx >= 2, 2]")
+            if not np.isfinite(w).all():
+                raise ValueError("wind must be finite")
+            self.wind = w
+
+        self.cell = float(cell)
+        self.margin = float(margin)
+        self._build_grid()
+
+    # ---------------------------------------------------------------------------------------------- reference scan
+    def find_mva_np(self, x, y):
+        """Airspace.find_mva (model.py:282-292) for arrays of points: first polygon index or -1."""
+        x = np.asarray(x, np.float64)
+        y = np.asarray(y, np.float64)
+        out = np.full(x.shape, -1, np.int32)
+        for m in range(len(self.rings) - 1, -1, -1):
+            b = self.mva_bounds[m]
+            hit = (b[0] <= x) & (x <= b[2]) & (b[1] <= y) & (y <= b[3])
+            hit &= ray_tracing_np(x, y, self.rings[m])
+            out[hit] = m
+        return out
+
+    # ---------------------------------------------------------------------------------------------- grid
+    def _build_grid(self):
+        cs, mg = self.cell, self.margin
+        x0, y0 = self.bbox[0], self.bbox[1]
+        nx = int(math.floor((self.bbox[2] - x0) / cs)) + 1
+        ny = int(math.floor((self.bbox[3] - y0) / cs)) + 1
+        self.grid_nx, self.grid_ny = nx, ny
+        self.grid_inv_cell = 1.0 / cs
+        edge_mask = np.zeros((ny, nx), np.uint32)
+        for m, ring in enumerate(self.rings):
+            for i in range(1, len(ring)):
+                px, py = ring[i - 1]
+                qx, qy = ring[i]
+                # cells whose (margin-expanded) rectangle overlaps the segment's bbox
+                ix0 = max(int(math.floor((min(px, qx) - mg - x0) / cs)) - 1, 0)
+                ix1 = min(int(math.floor((max(px, qx) + mg - x0) / cs)) + 1, nx - 1)
+                iy0 = max(int(math.floor((min(py, qy) - mg - y0) / cs)) - 1, 0)
+                iy1 = min(int(math.floor((max(py, qy) + mg - y0) / cs)) + 1, ny - 1)
+                if ix1 < ix0 or iy1 < iy0:
+                    continue
+                gx, gy = np.meshgrid(np.arange(ix0, ix1 + 1), np.arange(iy0, iy1 + 1))
+                rx0, rx1 = x0 + gx * cs - mg, x0 + (gx + 1) * cs + mg
+                ry0, ry1 = y0 + gy * cs - mg, y0 + (gy + 1) * cs + mg
+                overlap = (rx0 <= max(px, qx)) & (rx1 >= min(px, qx)) & (ry0 <= max(py, qy)) & (ry1 >= min(py, qy))
+                # separating axis = the segment's normal: all four corners strictly on one side -> no contact
+                ex, ey = qx - px, qy - py
+                tol = mg * (abs(ex) + abs(ey)) + 1e-12
+                c = np.stack([ex * (cy - py) - ey * (cx - px) for cx, cy in
+                              ((rx0, ry0), (rx1, ry0), (rx0, ry1), (rx1, ry1))])
+                touch = overlap & ~((c.min(0) > tol) | (c.max(0) < -tol))
+                edge_mask[iy0:iy1 + 1, ix0:ix1 + 1] |= np.where(touch, np.uint32(1 << m), np.uint32(0)).astype(np.uint32)
+        # status of every polygon at the cell centres (valid for polygons with no edge near the cell)
+        cxs = x0 + (np.arange(nx) + 0.5) * cs
+        cys = y0 + (np.arange(ny) + 0.5) * cs
+        gx, gy = np.meshgrid(cxs, cys)
+        contain_mask = np.zeros((ny, nx), np.uint32)
+        for m, ring in enumerate(self.rings):
+            inside = ray_tracing_np(gx.ravel(), gy.ravel(), ring).reshape(ny, nx)
+            contain_mask |= np.where(inside & ((edge_mask >> m) & 1 == 0), np.uint32(1 << m), np.uint32(0)).astype(np.uint32)
+        # first polygon (list order) that contains the whole cell; later polygons can never be the first match
+        lowest = contain_mask & (~contain_mask + np.uint32(1))           # lowest set bit (0 if none)
+        upto = np.where(lowest > 0, (lowest << np.uint32(1)) - np.uint32(1), np.uint32(0x7FFFFFFF)).astype(np.uint32)
+        cand = (edge_mask | contain_mask) & upto
+        mixed = (edge_mask & upto) != 0
+        first_idx = np.where(lowest > 0, np.log2(np.maximum(lowest, 1)).astype(np.int64) + 1, 0).astype(np.uint32)
+        self.grid_cell = np.ascontiguousarray(np.where(mixed, cand | np.uint32(0x80000000), first_idx).astype(np.uint32))
+        self.grid_mixed_fraction = float(mixed.mean())
+
+    def lookup_np(self, x, y):
+        """Host restatement of the kernel's find_mva (grid + exact fallback) — used by the CPU tests to check the
+        grid against the brute-force reference scan."""
+        x = np.asarray(x, np.float64)
+        y = np.asarray(y, np.float64)
+        out = np.full(x.shape, -1, np.int32)
+        inb = (x >= self.bbox[0]) & (x <= self.bbox[2]) & (y >= self.bbox[1]) & (y <= self.bbox[3])
+        with np.errstate(invalid='ignore'):
+            ix = np.clip(np.floor((x - self.bbox[0]) * self.grid_inv_cell), 0, self.grid_nx - 1)
+            iy = np.clip(np.floor((y - self.bbox[1]) * self.grid_inv_cell), 0, self.grid_ny - 1)
+        ix = np.where(inb, ix, 0).astype(np.int64)
+        iy = np.where(inb, iy, 0).astype(np.int64)
+        cell = self.grid_cell[iy, ix]
+        uniform = inb & ((cell & 0x80000000) == 0)
+        out[uniform] = cell[uniform].astype(np.int32) - 1
+        todo = inb & ~uniform
+        found = np.zeros(x.shape, bool)
+        for m in range(len(self.rings)):
+            b = self.mva_bounds[m]
+            sel = todo & ~found & (((cell >> m) & 1) == 1)
+            sel &= (b[0] <= x) & (x <= b[2]) & (b[1] <= y) & (y <= b[3])
+            if sel.any():
+                hit = np.zeros(x.shape, bool)
+                hit[sel] = ray_tracing_np(x[sel], y[sel], self.rings[m])
+                out[hit] = m
+                found |= hit
+        return out

@@ -1,0 +1,174 @@
+/*
+ * atc_b200.h — C ABI of the B200-native batched ATC approach-control environment step.
+ *
+ * This is the drop-in boundary for the reference's hot path AtcGym.step()/reset()
+ * (/root/reference/envs/atc/atc_gym.py:128-192, :337-365 and what they call in envs/atc/model.py).
+ * The reference is pure Python and has no FFI; the binding a maintainer adds is the ctypes stub shown in
+ * INTEGRATION.md (it is what atc_reinforcement_learning_b200/_native.py does).
+ *
+ * Rules of the boundary
+ *   - extern "C", plain pointers and sizes, no torch / C++ types in any signature.
+ *   - The CALLER owns every device buffer (PyTorch allocates them); the library allocates only its private copy
+ *     of the static sector at atc_create() and never allocates or frees afterwards, so atc_step()/atc_rollout()
+ *     are CUDA-graph capturable.  Kernels run on the caller-supplied stream (cudaStream_t passed as void*).
+ *   - No exceptions, no stdout: every entry point returns 0 on success or a negative AtcStatus;
+ *     atc_last_error() returns the message of the last failure on that handle (or the global one for atc_create).
+ *   - Invalid *actions* are not errors: like the reference (atc_gym.py:312-315) they cost the env -1.0 each.
+ *   - One handle per device; calls on one handle must be serialised by the caller; distinct handles are independent.
+ *
+ * Layouts (all row-major, contiguous)
+ *   state        double [5][n_env*n_ac]        planes x, y, h, phi, v        (reference: Airplane attributes, model.py:32-40)
+ *   actions      float  [n_env][n_ac][3]       v, h, phi in [-1, 1] (or MultiDiscrete indices as floats)
+ *   obs, raw_obs float  [n_env][n_ac][10]      atc_gym.py:262-277 ; raw_obs = info["original_state"]
+ *   reward       float  [n_env]                sum over the env's aircraft (atc_gym.py:137-185)
+ *   done         uint8  [n_env]
+ *   term         int32  [n_env]                bits 0-7 env code, bits 8+3a..10+3a per-aircraft code (AtcTermCode)
+ *   rollout buffers carry a leading [T] dimension.
+ */
+#ifndef ATC_B200_H
+#define ATC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATC_ABI_VERSION 1
+#define ATC_MAX_AIRCRAFT 8
+#define ATC_MAX_MVA 31
+#define ATC_OBS_DIM 10
+
+typedef enum AtcStatus {
+    ATC_OK = 0,
+    ATC_ERR_INVALID_ARGUMENT = -1,
+    ATC_ERR_CUDA = -2,
+    ATC_ERR_UNSUPPORTED = -3
+} AtcStatus;
+
+/* per-aircraft / per-env termination codes (reference branches: atc_gym.py:149-153, 156-161, 163-169, 171-173) */
+typedef enum AtcTermCode {
+    ATC_TERM_RUNNING = 0,
+    ATC_TERM_BELOW_MVA = 1,
+    ATC_TERM_LEFT_AIRSPACE = 2,
+    ATC_TERM_CAPTURED = 3,
+    ATC_TERM_TIMEOUT = 4,
+    ATC_TERM_SEPARATION = 5
+} AtcTermCode;
+
+/* Static sector, compiled on the host (atc_reinforcement_learning_b200/sector.py).  All pointers are HOST pointers;
+ * atc_create() copies what it needs to the device.  Replaces scenarios.py:7-207 + the constants derived in
+ * Corridor.__init__ (model.py:155-186) and AtcGym.__init__ (atc_gym.py:49-58, 88-110). */
+typedef struct AtcSectorDesc {
+    int32_t n_mva;                 /* <= ATC_MAX_MVA */
+    int32_t n_vertices;            /* total closed-ring vertices */
+    const double *ring_xy;         /* [n_vertices][2], rings closed, reference vertex order */
+    const int32_t *ring_off;       /* [n_mva + 1] */
+    const double *mva_height;      /* [n_mva] ft */
+    const double *mva_bounds;      /* [n_mva][4] minx, miny, maxx, maxy (model.py:268) */
+    double runway_x, runway_y, runway_h, phi_to_runway;
+    double faf[2];                 /* model.py:172 */
+    double normal[2];              /* model.py:165 */
+    double tri_h[8], tri_1[8], tri_2[8];   /* closed 4-vertex rings: corridor_horizontal / corridor1 / corridor2 */
+    double sin_to_runway, cos_to_runway;   /* rot_matrix(phi_to_runway).[0,1]^T  (model.py:219) */
+    double glide_tan;              /* tan(3 deg)  (model.py:205) */
+    double bbox[4];                /* union bounds (model.py:294-306) */
+    double world_max_distance;     /* atc_gym.py:58 */
+    double faf_mva;                /* atc_gym.py:49 */
+    float norm_min[ATC_OBS_DIM];   /* atc_gym.py:88-98 */
+    float norm_max[ATC_OBS_DIM];   /* atc_gym.py:99-110 */
+    int32_t n_entry;               /* scenarios.py:192-207 */
+    const double *entry_xyphi;     /* [n_entry][3] */
+    const int32_t *level_off;      /* [n_entry + 1] */
+    const int32_t *levels;         /* flight levels (x100 ft) */
+    /* exact MVA lookup accelerator: uniform grid over bbox, cell -> polygon or candidate mask */
+    int32_t grid_nx, grid_ny;
+    double grid_inv_cell;
+    const uint32_t *grid_cell;     /* [grid_ny][grid_nx]; bit31 clear: 0 = outside, k = polygon k-1;
+                                      bit31 set: bits 0-30 = candidate polygons, tested exactly in list order */
+    /* wind extension (not in the reference; README.md:64) — NULL / 0 = calm */
+    int32_t wind_gx, wind_gy;
+    const float *wind;             /* [wind_gy][wind_gx][2] knots (east, north), nodes on the bbox corners */
+} AtcSectorDesc;
+
+/* model.py:132-145 SimParameters + batch geometry */
+typedef struct AtcSimParams {
+    double timestep;               /* seconds */
+    int32_t reward_shaping;
+    int32_t normalize_state;
+    int32_t discrete_action_space;
+    int32_t normalize_reset_obs;   /* 0 = reference behaviour: reset() returns the RAW observation (atc_gym.py:351,365) */
+    int32_t n_env;
+    int32_t n_aircraft;            /* 1..ATC_MAX_AIRCRAFT */
+    int32_t track_actions;         /* maintain last_action / actions_taken (atc_gym.py:305-311) */
+    int32_t reserved;
+    uint64_t seed;                 /* spawn RNG key */
+    int64_t env_index_base;        /* global index of local env 0 (multi-GPU sharding) */
+} AtcSimParams;
+
+/* Persistent per-env state, DEVICE pointers owned by the caller. */
+typedef struct AtcBuffers {
+    double *state;                 /* [5][n_env*n_ac] */
+    double *last_action;           /* [3][n_env*n_ac] (track_actions) or NULL */
+    int32_t *timesteps;            /* [n_env]  atc_gym.py:39,135 */
+    int32_t *episodes;             /* [n_env]  episodes started (spawn RNG counter) */
+    double *ep_return;             /* [n_env]  total_reward (atc_gym.py:196) */
+    int32_t *actions_taken;        /* [n_env] (track_actions) or NULL */
+    double *last_ep_return;        /* [n_env]  return of the last finished episode (what the NCCL gather ships) */
+    int32_t *last_ep_len;          /* [n_env] */
+    int32_t *win_ring;             /* [n_env]  bit k = outcome of the k-th last finished episode (atc_gym.py:359-363) */
+} AtcBuffers;
+
+/* Per-call inputs/outputs, DEVICE pointers (atc_step / atc_rollout) or HOST pointers (the *_host variants). */
+typedef struct AtcStepIO {
+    const float *actions;          /* [T][n_env][n_ac][3] */
+    float *obs;                    /* [T][n_env][n_ac][10] */
+    float *raw_obs;                /* same shape or NULL */
+    float *reward;                 /* [T][n_env] */
+    uint8_t *done;                 /* [T][n_env] */
+    int32_t *term;                 /* [T][n_env] or NULL */
+} AtcStepIO;
+
+typedef struct AtcHandle AtcHandle;
+
+int atc_abi_version(void);
+
+/* Replaces AtcGym.__init__ (atc_gym.py:28-115) for a batch: validates, copies the sector to `device`. */
+int atc_create(const AtcSectorDesc *sector, const AtcSimParams *params, int device, AtcHandle **out);
+int atc_destroy(AtcHandle *h);
+
+/* Replaces AtcGym.reset (atc_gym.py:337-365) for the envs whose mask byte is non-zero (mask NULL = all).
+ * spawn NULL: entry point / level drawn by the counter-based device RNG; else explicit [n_env][n_ac][5]
+ * (x, y, h, phi, v) device array — the hook parity tests use to inject the reference's own spawn choices.
+ * obs (may be NULL) receives the reset observation of the reset envs only. */
+int atc_reset(AtcHandle *h, const AtcBuffers *b, const uint8_t *mask, const double *spawn, float *obs, void *stream);
+
+/* Replaces AtcGym.step (atc_gym.py:128-192): one fused kernel launch advancing every env by one step.
+ * autoreset != 0: finished envs are re-spawned inside the same launch and obs holds their reset observation
+ * (VecEnv convention); raw_obs always holds the pre-reset state. */
+int atc_step(AtcHandle *h, const AtcBuffers *b, const AtcStepIO *io, int autoreset, void *stream);
+
+/* T fused steps in ONE launch, state held in registers, autoreset on; io buffers carry the leading [T]. */
+int atc_rollout(AtcHandle *h, const AtcBuffers *b, const AtcStepIO *io, int n_steps, void *stream);
+
+/* End-to-end variants: io holds HOST pointers (pinned for full speed).  Actions are copied host->device, the
+ * step/rollout runs, results are copied device->host, all on `stream`, using the device staging buffers in
+ * `dev_io` (same shapes, caller-owned).  Returns after the stream is synchronised. */
+int atc_step_host(AtcHandle *h, const AtcBuffers *b, const AtcStepIO *host_io, const AtcStepIO *dev_io, int autoreset,
+                  void *stream);
+int atc_rollout_host(AtcHandle *h, const AtcBuffers *b, const AtcStepIO *host_io, const AtcStepIO *dev_io, int n_steps,
+                     void *stream);
+
+/* Geometry probes used by the parity tests (device arrays): MVA height in ft or -1 outside (model.py:282-292),
+ * and Runway.inside_corridor (model.py:188-231).  xy [n][2]; xyhphi [n][4]. */
+int atc_query_mva(AtcHandle *h, int n, const double *xy, int32_t *out, void *stream);
+int atc_query_corridor(AtcHandle *h, int n, const double *xyhphi, uint8_t *out, void *stream);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t atc_launch_count(const AtcHandle *h);
+const char *atc_last_error(const AtcHandle *h);   /* h may be NULL: last atc_create error */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATC_B200_H */
