@@ -37,7 +37,8 @@ class AtcSectorDesc(C.Structure):
         ('norm_min', C.c_float * OBS_DIM), ('norm_max', C.c_float * OBS_DIM),
         ('n_entry', C.c_int32), ('entry_xyphi', _dp), ('level_off', _ip), ('levels', _ip),
         ('grid_nx', C.c_int32), ('grid_ny', C.c_int32), ('grid_inv_cell', C.c_double),
-        ('grid_cell', C.POINTER(C.c_uint32)),
+        ('grid_cell', C.POINTER(C.c_uint16)), ('n_mixed', C.c_int32), ('n_prog', C.c_int32),
+        ('grid_prog_off', C.POINTER(C.c_uint32)), ('grid_prog', C.POINTER(C.c_uint16)),
         ('wind_gx', C.c_int32), ('wind_gy', C.c_int32), ('wind', _fp),
     ]
 
@@ -46,7 +47,7 @@ class AtcSimParams(C.Structure):
     _fields_ = [
         ('timestep', C.c_double), ('reward_shaping', C.c_int32), ('normalize_state', C.c_int32),
         ('discrete_action_space', C.c_int32), ('normalize_reset_obs', C.c_int32), ('n_env', C.c_int32),
-        ('n_aircraft', C.c_int32), ('track_actions', C.c_int32), ('reserved', C.c_int32), ('seed', C.c_uint64),
+        ('n_aircraft', C.c_int32), ('track_actions', C.c_int32), ('exact_math', C.c_int32), ('seed', C.c_uint64),
         ('env_index_base', C.c_int64),
     ]
 
@@ -146,7 +147,9 @@ def sector_desc(cs):
     d.entry_xyphi, d.level_off = _np_ptr(cs.entry_xyphi, C.c_double), _np_ptr(cs.level_off, C.c_int32)
     d.levels = _np_ptr(cs.levels, C.c_int32)
     d.grid_nx, d.grid_ny, d.grid_inv_cell = cs.grid_nx, cs.grid_ny, cs.grid_inv_cell
-    d.grid_cell = _np_ptr(cs.grid_cell, C.c_uint32)
+    d.grid_cell = _np_ptr(cs.grid_cell, C.c_uint16)
+    d.n_mixed, d.n_prog = len(cs.grid_prog_off), len(cs.grid_prog)
+    d.grid_prog_off, d.grid_prog = _np_ptr(cs.grid_prog_off, C.c_uint32), _np_ptr(cs.grid_prog, C.c_uint16)
     if cs.wind is not None:
         d.wind_gy, d.wind_gx = cs.wind.shape[0], cs.wind.shape[1]
         d.wind = _np_ptr(cs.wind, C.c_float)

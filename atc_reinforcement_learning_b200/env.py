@@ -43,7 +43,7 @@ class BatchedAtcEnv(object):
 
     def __init__(self, num_envs, num_aircraft=1, sim_parameters=None, scenario=None, device='cuda:0', seed=0,
                  wind=None, autoreset=True, track_actions=False, return_raw_obs=True, normalize_reset_obs=False,
-                 env_index_base=0, grid_cell=0.25):
+                 env_index_base=0, grid_cell=0.25, exact_math=False):
         self._handle = None
         if sim_parameters is None:
             sim_parameters = model.SimParameters(1)
@@ -69,6 +69,7 @@ class BatchedAtcEnv(object):
         self._seed = int(seed)
         self._env_index_base = int(env_index_base)
         self._normalize_reset_obs = bool(normalize_reset_obs)
+        self.exact_math = bool(exact_math)
 
         if sim_parameters.discrete_action_space:            # atc_gym.py:66-82
             self.action_space = spaces.MultiDiscrete([int((model.V_MAX - model.V_MIN) / 10), int(model.H_MAX / 100), 360])
@@ -103,6 +104,7 @@ class BatchedAtcEnv(object):
         p.normalize_reset_obs = int(self._normalize_reset_obs)
         p.n_env, p.n_aircraft = self.num_envs, self.num_aircraft
         p.track_actions = int(self.track_actions)
+        p.exact_math = int(self.exact_math)
         p.seed = self._seed & 0xFFFFFFFFFFFFFFFF
         p.env_index_base = self._env_index_base
         desc = nat.sector_desc(self.sector)

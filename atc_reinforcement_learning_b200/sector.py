@@ -171,13 +171,71 @@ class CompiledSector(object):
         upto = np.where(lowest > 0, (lowest << np.uint32(1)) - np.uint32(1), np.uint32(0x7FFFFFFF)).astype(np.uint32)
         cand = (edge_mask | contain_mask) & upto
         mixed = (edge_mask & upto) != 0
-        first_idx = np.where(lowest > 0, np.log2(np.maximum(lowest, 1)).astype(np.int64) + 1, 0).astype(np.uint32)
-        self.grid_cell = np.ascontiguousarray(np.where(mixed, cand | np.uint32(0x80000000), first_idx).astype(np.uint32))
+        first_idx = np.where(lowest > 0, np.log2(np.maximum(lowest, 1)).astype(np.int64) + 1, 0).astype(np.int64)
         self.grid_mixed_fraction = float(mixed.mean())
 
+        # ---- per-cell programs for the mixed cells
+        # For a candidate polygon only the edges that can interact with the cell's neighbourhood are kept:
+        #   * an edge whose y-range misses the cell's (margin-expanded) strip, or that lies wholly left of the cell,
+        #     can never satisfy the reference's crossing test (model.py:328-330) for a point of the cell -> dropped;
+        #   * an edge wholly right of the cell whose y-range spans the whole strip always crosses -> folded into a
+        #     parity bit;  everything else is tested exactly on the device.
+        grid = np.zeros((ny, nx), np.uint16)
+        uni = ~mixed
+        grid[uni] = first_idx[uni].astype(np.uint16)
+        prog, prog_off = [], []
+        iys, ixs = np.nonzero(mixed)
+        if len(iys) >= 0x8000:
+            raise ValueError("too many mixed cells (%d): use a coarser grid_cell" % len(iys))
+        edges = []      # per polygon: (global vertex index, ymin, ymax, xmin, xmax)
+        for m, ring in enumerate(self.rings):
+            el = []
+            for i in range(1, len(ring)):
+                (px, py), (qx, qy) = ring[i - 1], ring[i]
+                if py == qy:
+                    continue                                          # horizontal edges never cross
+                el.append((int(self.ring_off[m]) + i, min(py, qy), max(py, qy), min(px, qx), max(px, qx)))
+            edges.append(el)
+        for k, (iy, ix) in enumerate(zip(iys.tolist(), ixs.tolist())):
+            rx0, rx1 = x0 + ix * cs - mg, x0 + (ix + 1) * cs + mg
+            ry0, ry1 = y0 + iy * cs - mg, y0 + (iy + 1) * cs + mg
+            words, n_poly = [], 0
+            cm, em = int(cand[iy, ix]), int(edge_mask[iy, ix])
+            for m in range(len(self.rings)):
+                if not (cm >> m) & 1:
+                    continue
+                n_poly += 1
+                if not (em >> m) & 1:                                 # contains the whole cell: constant answer
+                    words.append(m | (1 << 5))
+                    continue
+                parity, keep = 0, []
+                for g, eymin, eymax, exmin, exmax in edges[m]:
+                    if eymax < ry0 or eymin > ry1 or exmax < rx0:
+                        continue
+                    if exmin > rx1 and eymin < ry0 and eymax > ry1:
+                        parity ^= 1
+                        continue
+                    keep.append(g)
+                if len(keep) > 255:
+                    raise ValueError("polygon with more than 255 edges near one cell")
+                bb = self.mva_bounds[m]
+                need_bbox = not (bb[0] < rx0 and bb[2] > rx1 and bb[1] < ry0 and bb[3] > ry1)
+                words.append(m | (parity << 5) | (int(need_bbox) << 6) | (len(keep) << 8))
+                words.extend(keep)
+            off = len(prog)
+            if off >= (1 << 26):
+                raise ValueError("MVA grid programs too large")
+            prog_off.append((n_poly << 26) | off)
+            prog.extend(words)
+            grid[iy, ix] = 0x8000 | k
+        self.grid_cell = np.ascontiguousarray(grid)
+        self.grid_prog_off = np.asarray(prog_off if prog_off else [0], np.uint32)
+        self.grid_prog = np.asarray(prog if prog else [0], np.uint16)
+        self.n_mixed = len(prog_off)
+
     def lookup_np(self, x, y):
-        """Host restatement of the kernel's find_mva (grid + exact fallback) — used by the CPU tests to check the
-        grid against the brute-force reference scan."""
+        """Host restatement of the kernel's find_mva (grid + per-cell programs) — used by the CPU tests to check the
+        accelerator against the brute-force reference scan."""
         x = np.asarray(x, np.float64)
         y = np.asarray(y, np.float64)
         out = np.full(x.shape, -1, np.int32)
@@ -188,17 +246,30 @@ class CompiledSector(object):
         ix = np.where(inb, ix, 0).astype(np.int64)
         iy = np.where(inb, iy, 0).astype(np.int64)
         cell = self.grid_cell[iy, ix]
-        uniform = inb & ((cell & 0x80000000) == 0)
+        uniform = inb & ((cell & 0x8000) == 0)
         out[uniform] = cell[uniform].astype(np.int32) - 1
-        todo = inb & ~uniform
-        found = np.zeros(x.shape, bool)
-        for m in range(len(self.rings)):
-            b = self.mva_bounds[m]
-            sel = todo & ~found & (((cell >> m) & 1) == 1)
-            sel &= (b[0] <= x) & (x <= b[2]) & (b[1] <= y) & (y <= b[3])
-            if sel.any():
-                hit = np.zeros(x.shape, bool)
-                hit[sel] = ray_tracing_np(x[sel], y[sel], self.rings[m])
-                out[hit] = m
-                found |= hit
+        ring = self.ring_xy
+        for i in np.nonzero(inb & ~uniform)[0]:
+            po = int(self.grid_prog_off[int(cell[i]) & 0x7FFF])
+            n_poly, p = po >> 26, po & 0x3FFFFFF
+            px, py = float(x[i]), float(y[i])
+            for _ in range(n_poly):
+                h = int(self.grid_prog[p]); p += 1
+                m, par, need_bbox, ne = h & 31, (h >> 5) & 1, (h >> 6) & 1, h >> 8
+                ok = True
+                if need_bbox:
+                    b = self.mva_bounds[m]
+                    ok = b[0] <= px <= b[2] and b[1] <= py <= b[3]
+                for j in range(ne):
+                    g = int(self.grid_prog[p + j])
+                    p1x, p1y = ring[g - 1]
+                    p2x, p2y = ring[g]
+                    if py > min(p1y, p2y) and py <= max(p1y, p2y) and px <= max(p1x, p2x):
+                        xints = (py - p1y) * (p2x - p1x) / (p2y - p1y) + p1x
+                        if p1x == p2x or px <= xints:
+                            par ^= 1
+                p += ne
+                if ok and par:
+                    out[i] = m
+                    break
         return out

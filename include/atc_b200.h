@@ -84,8 +84,14 @@ typedef struct AtcSectorDesc {
     /* exact MVA lookup accelerator: uniform grid over bbox, cell -> polygon or candidate mask */
     int32_t grid_nx, grid_ny;
     double grid_inv_cell;
-    const uint32_t *grid_cell;     /* [grid_ny][grid_nx]; bit31 clear: 0 = outside, k = polygon k-1;
-                                      bit31 set: bits 0-30 = candidate polygons, tested exactly in list order */
+    const uint16_t *grid_cell;     /* [grid_ny][grid_nx]; bit15 clear: 0 = outside, k = polygon k-1 for the whole cell;
+                                      bit15 set: bits 0-14 = index into grid_prog_off (a cell an edge passes near) */
+    int32_t n_mixed;               /* entries of grid_prog_off */
+    int32_t n_prog;                /* entries of grid_prog */
+    const uint32_t *grid_prog_off; /* [n_mixed]: bits 26-30 = candidate polygons, bits 0-25 = offset into grid_prog */
+    const uint16_t *grid_prog;     /* per candidate polygon, in list order: header (bits 0-4 polygon, bit 5 parity of
+                                      the edges that always cross, bit 6 bbox test needed, bits 8-15 edge count)
+                                      followed by the ring-vertex indices of the edges to test exactly */
     /* wind extension (not in the reference; README.md:64) — NULL / 0 = calm */
     int32_t wind_gx, wind_gy;
     const float *wind;             /* [wind_gy][wind_gx][2] knots (east, north), nodes on the bbox corners */
@@ -101,7 +107,8 @@ typedef struct AtcSimParams {
     int32_t n_env;
     int32_t n_aircraft;            /* 1..ATC_MAX_AIRCRAFT */
     int32_t track_actions;         /* maintain last_action / actions_taken (atc_gym.py:305-311) */
-    int32_t reserved;
+    int32_t exact_math;            /* 1: observation and reward shaping in float64 like the reference (slow);
+                                      0: float32 observation/shaping, float64 state and decisions (default) */
     uint64_t seed;                 /* spawn RNG key */
     int64_t env_index_base;        /* global index of local env 0 (multi-GPU sharding) */
 } AtcSimParams;

@@ -36,7 +36,8 @@ def expected_term(flags):
     return code
 
 
-def replay(tr, impl, state_atol=1e-9, reward_rtol=1e-9, obs_rtol=2e-7, obs_atol=1e-9, check_metrics=True):
+def replay(tr, impl, state_atol=1e-9, reward_rtol=1e-9, obs_rtol=2e-7, obs_atol=1e-9, check_metrics=True,
+           reward_atol=1e-12, return_rtol=1e-9, return_atol=1e-9):
     """impl interface (all numpy, n_ac == 1):
          impl.reset(mask[E] or None, spawn[E,1,5]) -> obs[E,1,10]
          impl.set_state(state[E,1,5], timesteps[E])
@@ -58,7 +59,7 @@ def replay(tr, impl, state_atol=1e-9, reward_rtol=1e-9, obs_rtol=2e-7, obs_atol=
         np.testing.assert_array_equal(ts, tr['timesteps'][t], err_msg=msg)
         np.testing.assert_array_equal(term & 0xFF, expected_term(tr['flags'][t]), err_msg=msg)
         np.testing.assert_allclose(st.reshape(E, 5), tr['state'][t], rtol=0, atol=state_atol, err_msg=msg)
-        np.testing.assert_allclose(rew, tr['reward'][t], rtol=reward_rtol, atol=1e-12, err_msg=msg)
+        np.testing.assert_allclose(rew, tr['reward'][t], rtol=reward_rtol, atol=reward_atol, err_msg=msg)
         np.testing.assert_allclose(obs.reshape(E, 10), tr['obs'][t], rtol=obs_rtol, atol=obs_atol, err_msg=msg)
         np.testing.assert_allclose(raw.reshape(E, 10), tr['raw_obs'][t], rtol=obs_rtol, atol=obs_atol, err_msg=msg)
         worst['state'] = max(worst['state'], float(np.abs(st.reshape(E, 5) - tr['state'][t]).max()))
@@ -68,7 +69,7 @@ def replay(tr, impl, state_atol=1e-9, reward_rtol=1e-9, obs_rtol=2e-7, obs_atol=
         if check_metrics:
             m = impl.metrics()
             np.testing.assert_array_equal(m['actions_taken'], tr['actions_taken'][t], err_msg=msg)
-            np.testing.assert_allclose(m['ep_return'], tr['total_reward'][t], rtol=1e-9, atol=1e-9, err_msg=msg)
+            np.testing.assert_allclose(m['ep_return'], tr['total_reward'][t], rtol=return_rtol, atol=return_atol, err_msg=msg)
         was_reset = done.astype(bool) & (np.abs(tr['spawn'][t]).sum(-1) > 0)
         if was_reset.any():
             ro = impl.reset(was_reset.astype(np.uint8), tr['spawn'][t].reshape(E, 1, 5))

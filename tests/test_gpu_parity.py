@@ -31,14 +31,14 @@ def scenario(name, random_entrypoints=False):
 class CudaImpl(object):
     """golden_util.replay adaptor over BatchedAtcEnv (device tensors in, numpy out)."""
 
-    def __init__(self, tr):
+    def __init__(self, tr, exact_math=False):
         from atc_reinforcement_learning_b200 import SimParameters
         m = tr['meta']
         E = tr['action'].shape[1]
         sp = SimParameters(m['dt'], reward_shaping=m['reward_shaping'], normalize_state=m['normalize_state'],
                            discrete_action_space=m['discrete'])
         self.env = make_env(E, 1, sp, scenario(m['scenario'], m['random_entrypoints']), autoreset=False,
-                            track_actions=True)
+                            track_actions=True, exact_math=exact_math)
 
     def reset(self, mask, spawn):
         return self.env.reset(mask, spawn).cpu().numpy()
@@ -63,10 +63,22 @@ class CudaImpl(object):
 
 @pytest.mark.parametrize('name', G.trace_names())
 def test_cuda_replays_reference_trace(name):
-    """Step-for-step against the live reference's recorded traces (every terminal branch, discrete actions, dt=5...)."""
+    """Step-for-step against the live reference's recorded traces (every terminal branch, discrete actions, dt=5...),
+    default arithmetic: float64 state/decisions, float32 observation/shaping.  Flags exact, state 1e-9, observation
+    and reward within north_star's 1e-5 (+1e-5 relative)."""
     tr = G.load_trace(name)
-    # reward is returned as float32: 6e-8 relative
-    worst = G.replay(tr, CudaImpl(tr), state_atol=1e-9, reward_rtol=2e-7, obs_rtol=OBS_RTOL, obs_atol=OBS_ATOL)
+    worst = G.replay(tr, CudaImpl(tr), state_atol=1e-9, reward_rtol=1e-5, reward_atol=1e-5, obs_rtol=OBS_RTOL,
+                     obs_atol=OBS_ATOL, return_rtol=1e-5, return_atol=1e-3)
+    print(name, worst)
+    assert worst['state'] <= 1e-9
+
+
+@pytest.mark.parametrize('name', G.trace_names())
+def test_cuda_exact_math_replays_reference_trace(name):
+    """exact_math=True: float64 + libm throughout; the only float32 rounding left is the returned reward (6e-8)."""
+    tr = G.load_trace(name)
+    worst = G.replay(tr, CudaImpl(tr, exact_math=True), state_atol=1e-9, reward_rtol=2e-7, reward_atol=1e-9,
+                     obs_rtol=2e-7, obs_atol=1e-7, return_rtol=1e-9, return_atol=1e-9)
     print(name, worst)
     assert worst['state'] <= 1e-9
 
@@ -111,11 +123,11 @@ def test_reference_unit_tests_on_cuda(tmp_path):
 
 # ------------------------------------------------------------------------------------------------ CUDA vs oracle
 def run_pair(N, A, T, seed, sector='LOWW', random_entrypoints=True, wind=None, dt=1.0, chunk=None, amp=1.0,
-             repeat=20, normalize_reset_obs=False, h_bias=False, spawn=None):
+             repeat=20, normalize_reset_obs=False, h_bias=False, spawn=None, exact_math=False):
     from atc_reinforcement_learning_b200 import SimParameters
     from oracle.oracle import Oracle
     env = make_env(N, A, SimParameters(dt), scenario(sector, random_entrypoints), seed=seed, wind=wind,
-                   track_actions=True, normalize_reset_obs=normalize_reset_obs)
+                   track_actions=True, normalize_reset_obs=normalize_reset_obs, exact_math=exact_math)
     ora = Oracle(sector, random_entrypoints, n_env=N, n_ac=A, dt=dt, seed=seed, wind=wind,
                  normalize_reset_obs=normalize_reset_obs)
     ora.reset()                       # the env constructor resets once (atc_gym.py:61)
@@ -149,8 +161,9 @@ def run_pair(N, A, T, seed, sector='LOWW', random_entrypoints=True, wind=None, d
     np.testing.assert_array_equal(env.win_ring.cpu().numpy(), m['win_ring'])
     np.testing.assert_array_equal(env.last_ep_len.cpu().numpy(), m['last_ep_len'])
     np.testing.assert_array_equal(env.actions_taken.cpu().numpy(), m['actions_taken'])
-    np.testing.assert_allclose(env.ep_return.cpu().numpy(), m['ep_return'], rtol=1e-9, atol=1e-9)
-    np.testing.assert_allclose(env.last_ep_return.cpu().numpy(), m['last_ep_return'], rtol=1e-9, atol=1e-9)
+    rt, at = (1e-9, 1e-9) if exact_math else (1e-5, 1e-3)
+    np.testing.assert_allclose(env.ep_return.cpu().numpy(), m['ep_return'], rtol=rt, atol=at)
+    np.testing.assert_allclose(env.last_ep_return.cpu().numpy(), m['last_ep_return'], rtol=rt, atol=at)
     codes = np.bincount((o_term & 0xFF)[o_done > 0], minlength=6)
     return {'dones': int(o_done.sum()), 'codes': codes.tolist(),
             'max_obs_err': float(np.abs(g_obs - o_obs).max()), 'max_rew_err': float(np.abs(g_rew - o_rew).max())}
@@ -194,6 +207,31 @@ def test_config4_16384x8_wind():
     r = run_pair(16384, 8, 64, seed=4, wind=wind)
     print(r)
     assert r['dones'] > 100
+
+
+def test_exact_math_vs_oracle_full_precision():
+    r = run_pair(4096, 4, 120, seed=41, exact_math=True)
+    print(r)
+    assert r['max_rew_err'] < 1e-5 and r['max_obs_err'] <= 4e-3      # reward: float32 rounding of the float64 sum
+
+
+def test_fast_normalisation_is_correctly_rounded():
+    """The default path divides by 0.5*max with a reciprocal + FMA correction (Markstein); it must give the same
+    float32 as IEEE division for every observation slot whose raw value is identical in both modes."""
+    from atc_reinforcement_learning_b200 import SimParameters
+    N, A, T = 16384, 4, 64
+    g = torch.Generator(device='cuda').manual_seed(77)
+    acts = (torch.rand(T, N, A, 3, device='cuda', generator=g) * 2 - 1)
+    ef = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=9)
+    ee = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=9, exact_math=True)
+    of, oe = ef.rollout(acts), ee.rollout(acts)
+    same_raw = [0, 1, 2, 3, 4, 5, 9]                      # casts of the float64 state: identical raw values
+    assert torch.equal(of[3]['original_state'][..., same_raw], oe[3]['original_state'][..., same_raw])
+    assert torch.equal(of[0][..., same_raw], oe[0][..., same_raw])
+    assert torch.equal(of[2], oe[2]) and torch.equal(of[3]['term_code'], oe[3]['term_code'])
+    assert torch.equal(ef.state, ee.state)
+    torch.testing.assert_close(of[0], oe[0], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(of[1], oe[1], rtol=1e-5, atol=1e-5)
 
 
 def test_odd_aircraft_counts_and_ragged_batches():
@@ -251,6 +289,12 @@ def test_full_size_step_equals_rollout_and_is_deterministic():
     e1 = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=5)
     e2 = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=5)
     e3 = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=5)
+    rng = np.random.RandomState(8)                       # dense traffic: separation resets inside the window
+    spawn = np.zeros((N, A, 5))
+    spawn[..., 0] = rng.uniform(30, 50, (N, A)); spawn[..., 1] = rng.uniform(38, 55, (N, A))
+    spawn[..., 2] = rng.uniform(8000, 11000, (N, A)); spawn[..., 3] = rng.uniform(0, 360, (N, A)); spawn[..., 4] = 250
+    for e in (e1, e2, e3):
+        e.reset(spawn=spawn)
     o1, r1, d1, t1 = _rollout_all(e1, acts, T)
     o2, r2, d2, t2 = _rollout_all(e2, acts, 7)
     steps = [e3.step(acts[t]) for t in range(T)]
@@ -260,7 +304,7 @@ def test_full_size_step_equals_rollout_and_is_deterministic():
         assert torch.equal(a, b)
     assert torch.equal(e1.state, e2.state) and torch.equal(e1.state, e3.state)
     assert torch.equal(e1.ep_return, e3.ep_return) and torch.equal(e1.episodes, e3.episodes)
-    assert int(d1.sum()) > 0
+    assert int(d1.sum()) > 1000
 
 
 def test_sharding_is_a_pure_partition():
