@@ -21,6 +21,24 @@ from .sector import CompiledSector
 TERM_NAMES = ('running', 'below_mva', 'left_airspace', 'captured', 'timeout', 'separation')
 
 
+_SECTOR_CACHE = {}
+
+
+def compile_sector_cached(scenario, cell, wind=None):
+    """CompiledSector is a pure function of the scenario data; building the fine MVA grid takes a couple of seconds,
+    so identical (scenario, cell) pairs share one compiled sector (wind grids are not cached)."""
+    if wind is not None:
+        return CompiledSector(scenario, cell=cell, wind=wind)
+    key = (float(cell),
+           tuple((m.height, tuple(m.area_as_list)) for m in scenario.mvas),
+           (scenario.runway.x, scenario.runway.y, scenario.runway.h, scenario.runway.phi_from_runway),
+           tuple((e.x, e.y, e.phi, tuple(e.levels)) for e in scenario.entrypoints))
+    cs = _SECTOR_CACHE.get(key)
+    if cs is None:
+        cs = _SECTOR_CACHE[key] = CompiledSector(scenario, cell=cell)
+    return cs
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
 
@@ -43,7 +61,7 @@ class BatchedAtcEnv(object):
 
     def __init__(self, num_envs, num_aircraft=1, sim_parameters=None, scenario=None, device='cuda:0', seed=0,
                  wind=None, autoreset=True, track_actions=False, return_raw_obs=True, normalize_reset_obs=False,
-                 env_index_base=0, grid_cell=0.25, exact_math=False):
+                 env_index_base=0, grid_cell=0.0625, exact_math=False):
         self._handle = None
         if sim_parameters is None:
             sim_parameters = model.SimParameters(1)
@@ -61,7 +79,7 @@ class BatchedAtcEnv(object):
         self.num_envs, self.num_aircraft = int(num_envs), int(num_aircraft)
         self._sim_parameters = sim_parameters
         self._scenario = scenario
-        self.sector = CompiledSector(scenario, cell=grid_cell, wind=wind)
+        self.sector = compile_sector_cached(scenario, grid_cell, wind)
         self.autoreset = bool(autoreset)
         self.track_actions = bool(track_actions)
         self.return_raw_obs = bool(return_raw_obs)

@@ -111,12 +111,14 @@ def cpu_oracle_rate(n_envs, n_aircraft, target_seconds, steps_hint=None, threads
     t = time.perf_counter()
     ora.rollout(a0)
     per_step = (time.perf_counter() - t) / T0
-    T = steps_hint or max(ACTION_REPEAT, int(target_seconds / max(per_step, 1e-9)))
-    T = min(T, 4000)
-    acts = np.repeat(rng.uniform(-1, 1, ((T + ACTION_REPEAT - 1) // ACTION_REPEAT, n_envs, n_aircraft, 3))
-                     .astype(np.float32), ACTION_REPEAT, 0)[:T]
+    chunk = 200
+    acts = np.repeat(rng.uniform(-1, 1, (chunk // ACTION_REPEAT, n_envs, n_aircraft, 3)).astype(np.float32),
+                     ACTION_REPEAT, 0)
+    n_chunks = steps_hint // chunk if steps_hint else max(1, int(target_seconds / max(per_step * chunk, 1e-9)))
+    T = n_chunks * chunk
     t = time.perf_counter()
-    ora.rollout(acts)
+    for _ in range(n_chunks):
+        ora.rollout(acts)
     sec = time.perf_counter() - t
     sample = '%d envs x %d aircraft x %d steps of the bench workload, %d OpenMP threads' % (n_envs, n_aircraft, T, cores)
     return n_envs * T / sec, cores, sample, sec
@@ -198,7 +200,7 @@ def run_gpu(args):
     torch.cuda.set_device(dev)
     N, A, TR = N_ENVS, N_AIRCRAFT, args.rollout
     env = BatchedAtcEnv(N, A, SimParameters(1), LOWW(random_entrypoints=True), device=dev, seed=0,
-                        env_index_base=rank * N, return_raw_obs=False)
+                        env_index_base=rank * N, return_raw_obs=False, grid_cell=args.grid_cell)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts = (torch.rand((TR + ACTION_REPEAT - 1) // ACTION_REPEAT, N, A, 3, device=dev, generator=g) * 2 - 1)
     acts = acts.repeat_interleave(ACTION_REPEAT, 0)[:TR].contiguous()
@@ -244,8 +246,8 @@ def run_gpu(args):
     ms_max = float(t.item())
     value = N * world * args.steps / (ms_max * 1e-3)
 
-    # ---- single-step-per-launch mode (the gym step() call), for context
-    step_ms = None
+    # ---- single-step-per-launch mode (the gym step() call), for context: eager launches and a CUDA graph of them
+    step_ms = graph_ms = None
     if not args.skip_extras:
         ks = min(args.steps, 2048)
         a1 = acts[0]
@@ -259,6 +261,28 @@ def run_gpu(args):
         ev1.record(stream)
         torch.cuda.synchronize(dev)
         step_ms = ev0.elapsed_time(ev1) / ks
+        try:                                           # the library never allocates -> step() is graph-capturable
+            gs = torch.cuda.Stream(dev)
+            gs.wait_stream(stream)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(gs):
+                env.step(a1, out=o1)
+                with torch.cuda.graph(graph, stream=gs):
+                    for i in range(TR):
+                        env.step(acts[i], out={k: v[i] for k, v in out.items()})
+            stream.wait_stream(gs)
+            torch.cuda.synchronize(dev)
+            reps = max(1, ks // TR)
+            graph.replay()
+            torch.cuda.synchronize(dev)
+            ev0.record(stream)
+            for _ in range(reps):
+                graph.replay()
+            ev1.record(stream)
+            torch.cuda.synchronize(dev)
+            graph_ms = ev0.elapsed_time(ev1) / (reps * TR)
+        except Exception as e:                         # pragma: no cover - reported, not fatal
+            print('cuda graph mode failed: %r' % (e,), file=sys.stderr)
 
     # ---- end to end through the host-buffer C-ABI entry point (pinned host memory both ways)
     e2e = None
@@ -290,7 +314,7 @@ def run_gpu(args):
     bytes_per_launch = bytes_rollout(A, TR) * N * (args.steps / launches)
     achieved = bytes_per_launch / avg_launch_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': 'atc_step_kernel<4,false,false> (rollout, T=%d)' % TR,
+                'traffic': None, 'peak_source': peak_src, 'kernel': 'atc_rollout_pipe_kernel<4,false,false,false> (rollout, T=%d)' % TR,
                 'algorithmic_bytes_per_env_step': bytes_rollout(A, TR), 'avg_launch_ms': avg_launch_s * 1e3}
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
@@ -310,7 +334,11 @@ def run_gpu(args):
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(gpu_launches), 'clocks': clocks,
         'single_step_launch': None if step_ms is None else {
             'ms_per_step': step_ms, 'value': N / (step_ms * 1e-3), 'unit': UNIT,
-            'roofline_frac': bytes_single_step(A) * N / (step_ms * 1e-3) / 1e9 / peak},
+            'roofline_frac': bytes_single_step(A) * N / (step_ms * 1e-3) / 1e9 / peak,
+            'cuda_graph_ms_per_step': graph_ms,
+            'cuda_graph_value': None if graph_ms is None else N / (graph_ms * 1e-3),
+            'cuda_graph_roofline_frac': None if graph_ms is None else
+            bytes_single_step(A) * N / (graph_ms * 1e-3) / 1e9 / peak},
         'nccl_gathers': gather.calls,
     }
     print(json.dumps(line), flush=True)
@@ -321,13 +349,14 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=16384)
-    ap.add_argument('--warmup', type=int, default=512)
+    ap.add_argument('--steps', type=int, default=65536)
+    ap.add_argument('--warmup', type=int, default=1024)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--rollout', type=int, default=128, help='env steps fused per kernel launch')
     ap.add_argument('--e2e-rollout', type=int, default=32)
     ap.add_argument('--e2e-steps', type=int, default=1024)
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
+    ap.add_argument('--grid-cell', type=float, default=0.0625, help='MVA lookup grid cell size in nm')
     ap.add_argument('--skip-extras', action='store_true', help='only the device-resident timing (used under ncu)')
     args = ap.parse_args()
     if args.warmup < 3:
