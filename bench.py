@@ -27,6 +27,14 @@ METRIC, UNIT = 'env-steps/sec', 'env-steps/s'
 ACTION_REPEAT = 20
 
 
+def host_threads():
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def bytes_rollout(A, T):
     """algorithmic bytes per env-step of the fused T-step rollout (float32 SoA accounting)."""
     return 52.0 * A + 8.0 + (40.0 * A + 8.0) / T
@@ -99,8 +107,7 @@ def cpu_oracle_rate(n_envs, n_aircraft, target_seconds, steps_hint=None, threads
     sample of the bench workload.  Returns (env_steps_per_s, cores, sample description, seconds)."""
     import numpy as np
     from oracle import oracle as O
-    if threads:
-        O.set_num_threads(threads)
+    O.set_num_threads(threads or host_threads())
     cores = O.num_threads()
     rng = np.random.RandomState(1234)
     ora = O.Oracle('LOWW', True, n_env=n_envs, n_ac=n_aircraft, seed=0)
@@ -133,6 +140,7 @@ def run_reference(args):
         return
     import numpy as np
     from oracle import oracle as O
+    O.set_num_threads(host_threads())
     cores = O.num_threads()
     # bounded sample per step: n_s envs of the 16384, sized so K + W steps take about 20 s
     n_probe = 1024
@@ -353,8 +361,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=1024)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--rollout', type=int, default=128, help='env steps fused per kernel launch')
-    ap.add_argument('--e2e-rollout', type=int, default=32)
-    ap.add_argument('--e2e-steps', type=int, default=1024)
+    ap.add_argument('--e2e-rollout', type=int, default=128)
+    ap.add_argument('--e2e-steps', type=int, default=2048)
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--grid-cell', type=float, default=0.0625, help='MVA lookup grid cell size in nm')
     ap.add_argument('--skip-extras', action='store_true', help='only the device-resident timing (used under ncu)')
