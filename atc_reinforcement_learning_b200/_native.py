@@ -38,7 +38,7 @@ class AtcSectorDesc(C.Structure):
         ('n_entry', C.c_int32), ('entry_xyphi', _dp), ('level_off', _ip), ('levels', _ip),
         ('grid_nx', C.c_int32), ('grid_ny', C.c_int32), ('grid_inv_cell', C.c_double),
         ('grid_cell', C.POINTER(C.c_uint16)), ('n_mixed', C.c_int32), ('n_prog', C.c_int32),
-        ('grid_prog_off', C.POINTER(C.c_uint32)), ('grid_prog', C.POINTER(C.c_uint16)),
+        ('grid_prog_off', C.POINTER(C.c_uint32)), ('grid_prog', C.POINTER(C.c_uint16)), ('grid_line', _dp),
         ('wind_gx', C.c_int32), ('wind_gy', C.c_int32), ('wind', _fp),
     ]
 
@@ -150,6 +150,7 @@ def sector_desc(cs):
     d.grid_cell = _np_ptr(cs.grid_cell, C.c_uint16)
     d.n_mixed, d.n_prog = len(cs.grid_prog_off), len(cs.grid_prog)
     d.grid_prog_off, d.grid_prog = _np_ptr(cs.grid_prog_off, C.c_uint32), _np_ptr(cs.grid_prog, C.c_uint16)
+    d.grid_line = _np_ptr(cs.grid_line, C.c_double)
     if cs.wind is not None:
         d.wind_gy, d.wind_gx = cs.wind.shape[0], cs.wind.shape[1]
         d.wind = _np_ptr(cs.wind, C.c_float)

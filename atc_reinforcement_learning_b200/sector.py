@@ -13,6 +13,7 @@ import numpy as np
 
 OBS_DIM = 10
 MAX_MVA = 31
+LINE_EPS = 1e-9     # nm: closer than this to a cell's boundary line -> exact program (kernel uses the same value)
 
 
 def ray_tracing_np(x, y, ring):
@@ -136,6 +137,7 @@ class CompiledSector(object):
         self.grid_nx, self.grid_ny = nx, ny
         self.grid_inv_cell = 1.0 / cs
         edge_mask = np.zeros((ny, nx), np.uint32)
+        touching = {}                 # (iy, ix) -> [(polygon, vertex index i)] of the edges that come near the cell
         for m, ring in enumerate(self.rings):
             for i in range(1, len(ring)):
                 px, py = ring[i - 1]
@@ -158,6 +160,8 @@ class CompiledSector(object):
                               ((rx0, ry0), (rx1, ry0), (rx0, ry1), (rx1, ry1))])
                 touch = overlap & ~((c.min(0) > tol) | (c.max(0) < -tol))
                 edge_mask[iy0:iy1 + 1, ix0:ix1 + 1] |= np.where(touch, np.uint32(1 << m), np.uint32(0)).astype(np.uint32)
+                for ty, tx in zip(*np.nonzero(touch)):
+                    touching.setdefault((iy0 + int(ty), ix0 + int(tx)), []).append((m, i))
         # status of every polygon at the cell centres (valid for polygons with no edge near the cell)
         cxs = x0 + (np.arange(nx) + 0.5) * cs
         cys = y0 + (np.arange(ny) + 0.5) * cs
@@ -233,6 +237,50 @@ class CompiledSector(object):
         self.grid_prog = np.asarray(prog if prog else [0], np.uint16)
         self.n_mixed = len(prog_off)
 
+        # ---- single-line records: in most mixed cells every nearby edge lies on ONE line (a shared
+        # polygon boundary crossing the cell, no vertex inside).  Polygon membership is then constant on each side of
+        # that line, and for a point farther than LINE_EPS from it the reference's ray cast equals the true membership,
+        # so the answer is a sign test; only points within LINE_EPS of the line run the exact program.
+        rec = np.zeros((max(self.n_mixed, 1), 4), np.float64)
+        rec_out = rec.view(np.int32).reshape(rec.shape[0], 8)      # out_pos, out_neg live in the 4th double's bits
+        probe_k, probe_side, probe_xy = [], [], []
+        n_line = 0
+        for k, (iy, ix) in enumerate(zip(iys.tolist(), ixs.tolist())):
+            tl = touching.get((iy, ix), [])
+            if not tl:
+                continue
+            rx0, rx1 = x0 + ix * cs - mg, x0 + (ix + 1) * cs + mg
+            ry0, ry1 = y0 + iy * cs - mg, y0 + (iy + 1) * cs + mg
+            m0, i0 = tl[0]
+            p, q = self.rings[m0][i0 - 1], self.rings[m0][i0]
+            ln = math.hypot(q[0] - p[0], q[1] - p[1])
+            if ln == 0.0:
+                continue
+            a, b = (q[1] - p[1]) / ln, -(q[0] - p[0]) / ln
+            c = -(a * p[0] + b * p[1])
+            ok = True
+            for m, i in tl:
+                for v in (self.rings[m][i - 1], self.rings[m][i]):
+                    if abs(a * v[0] + b * v[1] + c) > 1e-9:                      # not on the line
+                        ok = False
+                    if rx0 - mg <= v[0] <= rx1 + mg and ry0 - mg <= v[1] <= ry1 + mg:   # a vertex inside the cell
+                        ok = False
+            if not ok:
+                continue
+            corners = [(rx0, ry0), (rx1, ry0), (rx0, ry1), (rx1, ry1)]
+            d = [a * cx + b * cy + c for cx, cy in corners]
+            for side, sel in ((6, max), (7, min)):
+                dv = sel(d)
+                if abs(dv) > 1e-7 and (dv > 0) == (side == 6):               # else: no point of the cell on that side
+                    probe_k.append(k); probe_side.append(side); probe_xy.append(corners[d.index(dv)])
+            rec[k, 0], rec[k, 1], rec[k, 2] = a, b, c
+            n_line += 1
+        if probe_xy:                                   # one vectorised reference scan for all probe corners
+            pxy = np.asarray(probe_xy, np.float64)
+            rec_out[np.asarray(probe_k), np.asarray(probe_side)] = self.find_mva_np(pxy[:, 0], pxy[:, 1]) + 1
+        self.grid_line = np.ascontiguousarray(rec)
+        self.line_fraction = n_line / max(self.n_mixed, 1)
+
     def lookup_np(self, x, y):
         """Host restatement of the kernel's find_mva (grid + per-cell programs) — used by the CPU tests to check the
         accelerator against the brute-force reference scan."""
@@ -249,8 +297,19 @@ class CompiledSector(object):
         uniform = inb & ((cell & 0x8000) == 0)
         out[uniform] = cell[uniform].astype(np.int32) - 1
         ring = self.ring_xy
+        rec_out = self.grid_line.view(np.int32).reshape(-1, 8)
         for i in np.nonzero(inb & ~uniform)[0]:
-            po = int(self.grid_prog_off[int(cell[i]) & 0x7FFF])
+            k = int(cell[i]) & 0x7FFF
+            a, b, c = self.grid_line[k, :3]
+            if a != 0.0 or b != 0.0:
+                d = a * float(x[i]) + b * float(y[i]) + c
+                if d > LINE_EPS:
+                    out[i] = rec_out[k, 6] - 1
+                    continue
+                if d < -LINE_EPS:
+                    out[i] = rec_out[k, 7] - 1
+                    continue
+            po = int(self.grid_prog_off[k])
             n_poly, p = po >> 26, po & 0x3FFFFFF
             px, py = float(x[i]), float(y[i])
             for _ in range(n_poly):

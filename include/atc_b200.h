@@ -92,6 +92,10 @@ typedef struct AtcSectorDesc {
     const uint16_t *grid_prog;     /* per candidate polygon, in list order: header (bits 0-4 polygon, bit 5 parity of
                                       the edges that always cross, bit 6 bbox test needed, bits 8-15 edge count)
                                       followed by the ring-vertex indices of the edges to test exactly */
+    const double *grid_line;       /* [n_mixed][4]: a, b, c of the single boundary line crossing the cell (a = b = 0:
+                                      none) with a*a + b*b = 1, and two int32 in the 4th double: answer (polygon + 1,
+                                      0 = outside) on the positive / negative side.  Points farther than 1e-9 nm from
+                                      the line take the answer, the others run the exact program. */
     /* wind extension (not in the reference; README.md:64) — NULL / 0 = calm */
     int32_t wind_gx, wind_gy;
     const float *wind;             /* [wind_gy][wind_gx][2] knots (east, north), nodes on the bbox corners */
