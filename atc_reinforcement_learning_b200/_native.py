@@ -18,7 +18,8 @@ MAX_AIRCRAFT = 8
 OBS_DIM = 10
 
 EXPORTS = ['atc_abi_version', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
-           'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error']
+           'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
+           'atc_obs_stats_update', 'atc_obs_normalize']
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -110,6 +111,10 @@ def lib():
     L.atc_rollout_host.argtypes = [vp, C.POINTER(AtcBuffers), C.POINTER(AtcStepIO), C.POINTER(AtcStepIO), C.c_int, vp]
     L.atc_query_mva.argtypes = [vp, C.c_int, vp, vp, vp]
     L.atc_query_corridor.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.atc_obs_stats_update.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
+    L.atc_obs_normalize.argtypes = [vp, C.c_int64, C.c_int32, vp, C.c_double, C.c_double, vp, vp]
+    L.atc_obs_stats_update.restype = C.c_int
+    L.atc_obs_normalize.restype = C.c_int
     L.atc_launch_count.argtypes = [vp]
     L.atc_launch_count.restype = C.c_int64
     L.atc_last_error.argtypes = [vp]

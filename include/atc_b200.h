@@ -175,6 +175,20 @@ int atc_rollout_host(AtcHandle *h, const AtcBuffers *b, const AtcStepIO *host_io
 int atc_query_mva(AtcHandle *h, int n, const double *xy, int32_t *out, void *stream);
 int atc_query_corridor(AtcHandle *h, int n, const double *xyhphi, uint8_t *out, void *stream);
 
+/* Next-row component: running observation statistics + normalisation + finiteness check on the
+ * device, the role stable-baselines' VecNormalize / VecCheckNan play around the env in the reference's tuner
+ * (/root/reference/learning/tune_hyperparameters.py:94-97).  Stateless: all buffers are caller-owned device memory.
+ *   x        float [n_rows][dim]
+ *   rms      double [2*dim + 1]   running mean[dim], var[dim], count   (initialise: mean 0, var 1, count 1e-4)
+ *   scratch  double [2*dim + 2]   zero-initialised by the caller once; left zeroed by every call
+ *   nonfinite int32 [1]           set to 1 if x holds a NaN / Inf (never cleared by the library)
+ * atc_obs_stats_update merges the batch moments into rms (Chan et al. parallel update, float64);
+ * atc_obs_normalize writes clip((x - mean) / sqrt(var + epsilon), -clip, clip). */
+int atc_obs_stats_update(const float *x, int64_t n_rows, int32_t dim, double *rms, double *scratch, int32_t *nonfinite,
+                         void *stream);
+int atc_obs_normalize(const float *x, int64_t n_rows, int32_t dim, const double *rms, double epsilon, double clip,
+                      float *out, void *stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t atc_launch_count(const AtcHandle *h);
 const char *atc_last_error(const AtcHandle *h);   /* h may be NULL: last atc_create error */
