@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libatc_b200.so')
 INCLUDE = os.path.join(ROOT, 'include')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_AIRCRAFT = 8
 OBS_DIM = 10
 
@@ -38,6 +38,7 @@ class AtcSectorDesc(C.Structure):
         ('norm_min', C.c_float * OBS_DIM), ('norm_max', C.c_float * OBS_DIM),
         ('n_entry', C.c_int32), ('entry_xyphi', _dp), ('level_off', _ip), ('levels', _ip),
         ('grid_nx', C.c_int32), ('grid_ny', C.c_int32), ('grid_inv_cell', C.c_double),
+        ('grid_x0', C.c_double), ('grid_y0', C.c_double),
         ('grid_cell', C.POINTER(C.c_uint16)), ('n_mixed', C.c_int32), ('n_prog', C.c_int32),
         ('grid_prog_off', C.POINTER(C.c_uint32)), ('grid_prog', C.POINTER(C.c_uint16)), ('grid_line', _dp),
         ('wind_gx', C.c_int32), ('wind_gy', C.c_int32), ('wind', _fp),
@@ -152,6 +153,7 @@ def sector_desc(cs):
     d.entry_xyphi, d.level_off = _np_ptr(cs.entry_xyphi, C.c_double), _np_ptr(cs.level_off, C.c_int32)
     d.levels = _np_ptr(cs.levels, C.c_int32)
     d.grid_nx, d.grid_ny, d.grid_inv_cell = cs.grid_nx, cs.grid_ny, cs.grid_inv_cell
+    d.grid_x0, d.grid_y0 = cs.grid_x0, cs.grid_y0
     d.grid_cell = _np_ptr(cs.grid_cell, C.c_uint16)
     d.n_mixed, d.n_prog = len(cs.grid_prog_off), len(cs.grid_prog)
     d.grid_prog_off, d.grid_prog = _np_ptr(cs.grid_prog_off, C.c_uint32), _np_ptr(cs.grid_prog, C.c_uint16)

@@ -13,6 +13,7 @@ import numpy as np
 
 OBS_DIM = 10
 MAX_MVA = 31
+GRID_PAD = 2        # rings of cells around the bbox: the outer one is always "outside", so clamping is safe
 LINE_EPS = 1e-9     # nm: closer than this to a cell's boundary line -> exact program (kernel uses the same value)
 
 
@@ -41,7 +42,7 @@ def _rot_apply(phi_deg, vx, vy):
 
 
 class CompiledSector(object):
-    def __init__(self, scenario, cell=0.25, margin=1e-6, wind=None):
+    def __init__(self, scenario, cell=0.25, margin=None, wind=None):
         mvas = scenario.mvas
         if len(mvas) > MAX_MVA:
             raise ValueError("at most %d MVA polygons are supported" % MAX_MVA)
@@ -112,6 +113,14 @@ class CompiledSector(object):
             self.wind = w
 
         self.cell = float(cell)
+        # The kernel finds the grid cell of a point from its float32 coordinates (one FFMA per axis), so the cell it
+        # picks may be the neighbour of the true one when the point is within the float32 error of a cell border.
+        # Every cell's stored answer / program is therefore valid on the cell expanded by `margin`, chosen as 4x a
+        # bound of that error: rounding of the coordinate, of the folded offset and of the FFMA result.
+        if margin is None:
+            n_cells = max(self.bbox[2] - self.bbox[0], self.bbox[3] - self.bbox[1]) / self.cell + 2 * GRID_PAD + 1
+            err = 2.0 ** -24 * (float(np.abs(self.bbox).max()) + 2.0 * self.cell * n_cells)
+            margin = max(1e-6, 4.0 * err)
         self.margin = float(margin)
         self._build_grid()
 
@@ -131,10 +140,12 @@ class CompiledSector(object):
     # ---------------------------------------------------------------------------------------------- grid
     def _build_grid(self):
         cs, mg = self.cell, self.margin
-        x0, y0 = self.bbox[0], self.bbox[1]
-        nx = int(math.floor((self.bbox[2] - x0) / cs)) + 1
-        ny = int(math.floor((self.bbox[3] - y0) / cs)) + 1
+        # the grid starts GRID_PAD cells outside the bbox and ends GRID_PAD cells beyond it
+        x0, y0 = self.bbox[0] - GRID_PAD * cs, self.bbox[1] - GRID_PAD * cs
+        nx = int(math.floor((self.bbox[2] - x0) / cs)) + 1 + GRID_PAD
+        ny = int(math.floor((self.bbox[3] - y0) / cs)) + 1 + GRID_PAD
         self.grid_nx, self.grid_ny = nx, ny
+        self.grid_x0, self.grid_y0 = float(x0), float(y0)
         self.grid_inv_cell = 1.0 / cs
         edge_mask = np.zeros((ny, nx), np.uint32)
         touching = {}                 # (iy, ix) -> [(polygon, vertex index i)] of the edges that come near the cell
@@ -232,6 +243,9 @@ class CompiledSector(object):
             prog_off.append((n_poly << 26) | off)
             prog.extend(words)
             grid[iy, ix] = 0x8000 | k
+        border = np.concatenate([grid[0], grid[-1], grid[:, 0], grid[:, -1]])
+        if border.any():
+            raise AssertionError("MVA grid: the outermost ring of cells must be uniformly outside")
         self.grid_cell = np.ascontiguousarray(grid)
         self.grid_prog_off = np.asarray(prog_off if prog_off else [0], np.uint32)
         self.grid_prog = np.asarray(prog if prog else [0], np.uint16)
@@ -281,24 +295,39 @@ class CompiledSector(object):
         self.grid_line = np.ascontiguousarray(rec)
         self.line_fraction = n_line / max(self.n_mixed, 1)
 
-    def lookup_np(self, x, y):
+    def cell_index_np(self, x, y):
+        """The kernel's float32 cell index (mva_cell in csrc/atc_kernels.cu): fx = xf * scale + off clamped to the
+        grid, truncated.  NaN clamps to cell 0 (outside).  numpy has no FMA: the product is formed in float64 and
+        rounded once, which is what the FFMA does."""
+        sc = np.float32(self.grid_inv_cell)
+        ox = np.float32(-self.grid_x0 * self.grid_inv_cell)
+        oy = np.float32(-self.grid_y0 * self.grid_inv_cell)
+        with np.errstate(invalid='ignore'):
+            xf = np.asarray(x, np.float64).astype(np.float32)
+            yf = np.asarray(y, np.float64).astype(np.float32)
+            fx = (xf.astype(np.float64) * np.float64(sc) + np.float64(ox)).astype(np.float32)
+            fy = (yf.astype(np.float64) * np.float64(sc) + np.float64(oy)).astype(np.float32)
+            fx = np.fmin(np.fmax(fx, np.float32(0)), np.float32(self.grid_nx - 1))
+            fy = np.fmin(np.fmax(fy, np.float32(0)), np.float32(self.grid_ny - 1))
+        return fx.astype(np.int64), fy.astype(np.int64)
+
+    def lookup_np(self, x, y, cells=None):
         """Host restatement of the kernel's find_mva (grid + per-cell programs) — used by the CPU tests to check the
-        accelerator against the brute-force reference scan."""
+        accelerator against the brute-force reference scan.  `cells` = (ix, iy) overrides the cell choice (the tests
+        use it to show that every cell within `margin` of a point gives the same, exact answer)."""
         x = np.asarray(x, np.float64)
         y = np.asarray(y, np.float64)
         out = np.full(x.shape, -1, np.int32)
-        inb = (x >= self.bbox[0]) & (x <= self.bbox[2]) & (y >= self.bbox[1]) & (y <= self.bbox[3])
-        with np.errstate(invalid='ignore'):
-            ix = np.clip(np.floor((x - self.bbox[0]) * self.grid_inv_cell), 0, self.grid_nx - 1)
-            iy = np.clip(np.floor((y - self.bbox[1]) * self.grid_inv_cell), 0, self.grid_ny - 1)
-        ix = np.where(inb, ix, 0).astype(np.int64)
-        iy = np.where(inb, iy, 0).astype(np.int64)
+        if cells is None:
+            ix, iy = self.cell_index_np(x, y)
+        else:
+            ix, iy = cells
         cell = self.grid_cell[iy, ix]
-        uniform = inb & ((cell & 0x8000) == 0)
+        uniform = (cell & 0x8000) == 0
         out[uniform] = cell[uniform].astype(np.int32) - 1
         ring = self.ring_xy
         rec_out = self.grid_line.view(np.int32).reshape(-1, 8)
-        for i in np.nonzero(inb & ~uniform)[0]:
+        for i in np.nonzero(~uniform)[0]:
             k = int(cell[i]) & 0x7FFF
             a, b, c = self.grid_line[k, :3]
             if a != 0.0 or b != 0.0:

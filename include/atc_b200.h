@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ATC_ABI_VERSION 1
+#define ATC_ABI_VERSION 2
 #define ATC_MAX_AIRCRAFT 8
 #define ATC_MAX_MVA 31
 #define ATC_OBS_DIM 10
@@ -81,9 +81,13 @@ typedef struct AtcSectorDesc {
     const double *entry_xyphi;     /* [n_entry][3] */
     const int32_t *level_off;      /* [n_entry + 1] */
     const int32_t *levels;         /* flight levels (x100 ft) */
-    /* exact MVA lookup accelerator: uniform grid over bbox, cell -> polygon or candidate mask */
+    /* exact MVA lookup accelerator: uniform grid whose cell (0, 0) starts at (grid_x0, grid_y0), two
+       cells outside the bbox, and which ends two cells beyond it; the outermost ring of cells must be "outside" (0).
+       The kernels pick the cell from float32 coordinates, so every cell's entry must hold on the cell grown by the
+       float32 index error (sector.py `margin`). */
     int32_t grid_nx, grid_ny;
     double grid_inv_cell;
+    double grid_x0, grid_y0;
     const uint16_t *grid_cell;     /* [grid_ny][grid_nx]; bit15 clear: 0 = outside, k = polygon k-1 for the whole cell;
                                       bit15 set: bits 0-14 = index into grid_prog_off (a cell an edge passes near) */
     int32_t n_mixed;               /* entries of grid_prog_off */

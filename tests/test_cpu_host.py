@@ -115,8 +115,8 @@ def test_mva_grid_is_exact(scn, cell):
     n = 300000
     pts = [np.stack([rng.uniform(cs.bbox[0] - 1, cs.bbox[2] + 1, n), rng.uniform(cs.bbox[1] - 1, cs.bbox[3] + 1, n)], 1)]
     # cell borders / corners, +- a few ulps and +- 1e-9
-    gx = cs.bbox[0] + np.arange(cs.grid_nx + 1) * cell
-    gy = cs.bbox[1] + np.arange(cs.grid_ny + 1) * cell
+    gx = cs.grid_x0 + np.arange(cs.grid_nx + 1) * cell
+    gy = cs.grid_y0 + np.arange(cs.grid_ny + 1) * cell
     bx = rng.choice(gx, 40000)
     by = rng.choice(gy, 40000)
     for d in (0.0, 1e-9, -1e-9):
@@ -134,7 +134,25 @@ def test_mva_grid_is_exact(scn, cell):
             for d in (0.0, 1e-12, -1e-12, 1e-7, -1e-7, 1e-3, -1e-3):
                 pts.append(on + d * nrm)
     pts = np.concatenate(pts, 0)
-    np.testing.assert_array_equal(cs.lookup_np(pts[:, 0], pts[:, 1]), ora.mva_index(pts))
+    want = ora.mva_index(pts)
+    np.testing.assert_array_equal(cs.lookup_np(pts[:, 0], pts[:, 1]), want)
+    # The kernel picks the cell from float32 coordinates, so near a border it may take the neighbour: every cell whose
+    # rectangle comes within `margin` of the point must give the same exact answer, and the float32 index must be one
+    # of those cells.
+    mg = cs.margin
+    ix32, iy32 = cs.cell_index_np(pts[:, 0], pts[:, 1])
+    inside = ((pts[:, 0] > cs.grid_x0 + cell) & (pts[:, 0] < cs.grid_x0 + (cs.grid_nx - 1) * cell) &
+              (pts[:, 1] > cs.grid_y0 + cell) & (pts[:, 1] < cs.grid_y0 + (cs.grid_ny - 1) * cell))
+    lo_x = np.floor((pts[:, 0] - mg - cs.grid_x0) / cell).astype(np.int64)
+    hi_x = np.floor((pts[:, 0] + mg - cs.grid_x0) / cell).astype(np.int64)
+    lo_y = np.floor((pts[:, 1] - mg - cs.grid_y0) / cell).astype(np.int64)
+    hi_y = np.floor((pts[:, 1] + mg - cs.grid_y0) / cell).astype(np.int64)
+    assert ((ix32 >= lo_x) & (ix32 <= hi_x) & (iy32 >= lo_y) & (iy32 <= hi_y))[inside].all()
+    amb = np.nonzero(inside & ((lo_x != hi_x) | (lo_y != hi_y)))[0]
+    assert len(amb) > 1000
+    for cx, cy in ((lo_x, lo_y), (hi_x, lo_y), (lo_x, hi_y), (hi_x, hi_y)):
+        got = cs.lookup_np(pts[amb, 0], pts[amb, 1], cells=(cx[amb], cy[amb]))
+        np.testing.assert_array_equal(got, want[amb])
     # NaN / inf are "outside"
     bad = np.array([[np.nan, 10.0], [10.0, np.nan], [np.inf, 10.0], [-np.inf, -np.inf]])
     assert (cs.lookup_np(bad[:, 0], bad[:, 1]) == -1).all() and (ora.mva_index(bad) == -1).all()

@@ -215,9 +215,10 @@ def test_exact_math_vs_oracle_full_precision():
     assert r['max_rew_err'] < 1e-5 and r['max_obs_err'] <= 4e-3      # reward: float32 rounding of the float64 sum
 
 
-def test_fast_normalisation_is_correctly_rounded():
-    """The default path divides by 0.5*max with a reciprocal + FMA correction (Markstein); it must give the same
-    float32 as IEEE division for every observation slot whose raw value is identical in both modes."""
+def test_fast_normalisation_stays_within_float32_rounding():
+    """The default path normalises with one FFMA per slot (v * 1/half - (min + half)/half) instead of the reference's
+    two subtractions and a division (atc_gym.py:187-189).  For the slots whose raw value is identical in both modes
+    the result must stay within a few float32 roundings of the exact_math path (values are in [-1, 1])."""
     from atc_reinforcement_learning_b200 import SimParameters
     N, A, T = 16384, 4, 64
     g = torch.Generator(device='cuda').manual_seed(77)
@@ -227,7 +228,9 @@ def test_fast_normalisation_is_correctly_rounded():
     of, oe = ef.rollout(acts), ee.rollout(acts)
     same_raw = [0, 1, 2, 3, 4, 5, 9]                      # casts of the float64 state: identical raw values
     assert torch.equal(of[3]['original_state'][..., same_raw], oe[3]['original_state'][..., same_raw])
-    assert torch.equal(of[0][..., same_raw], oe[0][..., same_raw])
+    # rows of freshly reset envs hold raw (un-normalised) values, identical in both modes; the others are in [-1, 1]
+    err = (of[0][..., same_raw].double() - oe[0][..., same_raw].double()).abs()
+    assert float(err.max()) <= 4e-7, float(err.max())
     assert torch.equal(of[2], oe[2]) and torch.equal(of[3]['term_code'], oe[3]['term_code'])
     assert torch.equal(ef.state, ee.state)
     torch.testing.assert_close(of[0], oe[0], rtol=1e-5, atol=1e-5)
