@@ -35,13 +35,15 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def bytes_rollout(A, T):
-    """algorithmic bytes per env-step of the fused T-step rollout (float32 SoA accounting)."""
-    return 52.0 * A + 8.0 + (40.0 * A + 8.0) / T
+def bytes_rollout(A, T, raw_obs=False):
+    """algorithmic bytes per env-step of the fused T-step rollout (float32 SoA accounting): actions in,
+    observation / reward / done out every step, state once per launch; + 40 B per aircraft when the step also writes
+    info["original_state"] (the raw observation the reference returns with every step, atc_gym.py:192)."""
+    return 52.0 * A + 8.0 + (40.0 * A + 8.0) / T + (40.0 * A if raw_obs else 0.0)
 
 
-def bytes_single_step(A):
-    return 92.0 * A + 16.0
+def bytes_single_step(A, raw_obs=False):
+    return 92.0 * A + 16.0 + (40.0 * A if raw_obs else 0.0)
 
 
 def measured_peaks():
@@ -56,7 +58,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.005):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -82,21 +84,31 @@ class ClockSampler(threading.Thread):
             getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
             getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
         }
+        self.names = names
         while not self._stop_evt.is_set():
             try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.samples.append((time.perf_counter(), mhz, r))
             except Exception:
                 pass
             time.sleep(self.period)
 
+    def mark_begin(self):
+        """Start of the timed region: earlier samples (warm-up) are dropped by stop()."""
+        self.t_begin = time.perf_counter()
+
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
-        s = sorted(self.samples)
+        if not self.ok:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        kept = [x for x in self.samples if x[0] >= getattr(self, 't_begin', 0.0)] or self.samples[-1:]
+        s = sorted(x[1] for x in kept)
+        for _, _, r in kept:
+            for bit, name in self.names.items():
+                if r & bit:
+                    self.reasons.add(name)
         return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
                 'samples': len(s)}
 
@@ -178,7 +190,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, extra=None):
@@ -186,8 +198,11 @@ def workload_config(args, extra=None):
                      'separation, auto-reset, U(-1,1) actions re-sampled every %d steps (BASELINE.json configs[2])'
                      % (N_ENVS, N_AIRCRAFT, ACTION_REPEAT),
          'envs_per_gpu': N_ENVS, 'aircraft_per_env': N_AIRCRAFT, 'rollout_steps_per_launch': args.rollout,
+         'step_outputs': 'obs + info[original_state] + reward + done + term' if args.raw_obs else
+                         'obs + reward + done + term (no info[original_state])',
          'l2': 'per-launch working set (actions %.0f MB in + observations %.0f MB out) exceeds the 126 MB L2; no flush'
-               % (args.rollout * N_ENVS * N_AIRCRAFT * 12 / 1e6, args.rollout * N_ENVS * N_AIRCRAFT * 40 / 1e6)}
+               % (args.rollout * N_ENVS * N_AIRCRAFT * 12 / 1e6,
+                  args.rollout * N_ENVS * N_AIRCRAFT * 40 * (2 if args.raw_obs else 1) / 1e6)}
     if extra:
         c.update(extra)
     return c
@@ -207,13 +222,14 @@ def run_gpu(args):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     N, A, TR = N_ENVS, N_AIRCRAFT, args.rollout
+    RAW = bool(args.raw_obs)
     env = BatchedAtcEnv(N, A, SimParameters(1), LOWW(random_entrypoints=True), device=dev, seed=0,
-                        env_index_base=rank * N, return_raw_obs=False, grid_cell=args.grid_cell)
+                        env_index_base=rank * N, return_raw_obs=RAW, grid_cell=args.grid_cell)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts = (torch.rand((TR + ACTION_REPEAT - 1) // ACTION_REPEAT, N, A, 3, device=dev, generator=g) * 2 - 1)
     acts = acts.repeat_interleave(ACTION_REPEAT, 0)[:TR].contiguous()
     out = env._alloc_io((TR,))
-    gather = ReturnGather(N, dev)
+    gather = ReturnGather(N, dev, overlap=None if args.gather_overlap < 0 else bool(args.gather_overlap))
     stream = torch.cuda.current_stream(dev)
 
     def run_steps(n):
@@ -232,12 +248,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # every rank samples its own GPU's clocks; the sampler (NVML init takes milliseconds) is up before the barrier so
+    # that all ranks enter the timed region together, and only samples taken inside the region are kept
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     run_steps(args.warmup)
     gather.wait()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
+    sampler.mark_begin()
     l0 = env.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -246,12 +264,20 @@ def run_gpu(args):
     gather.wait()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
     gpu_launches = env.launch_count - l0
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    ms_ranks = [ms]
     if world > 1:
+        allms = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allms, t)
+        ms_ranks = [float(x.item()) for x in allms]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
+    clocks_ranks = [clocks]
+    if world > 1:
+        clocks_ranks = [None] * world
+        dist.all_gather_object(clocks_ranks, clocks)
     value = N * world * args.steps / (ms_max * 1e-3)
 
     # ---- single-step-per-launch mode (the gym step() call), for context: eager launches and a CUDA graph of them
@@ -269,6 +295,7 @@ def run_gpu(args):
         ev1.record(stream)
         torch.cuda.synchronize(dev)
         step_ms = ev0.elapsed_time(ev1) / ks
+        GT = min(TR, 128)                              # steps captured into one CUDA graph
         try:                                           # the library never allocates -> step() is graph-capturable
             gs = torch.cuda.Stream(dev)
             gs.wait_stream(stream)
@@ -276,11 +303,11 @@ def run_gpu(args):
             with torch.cuda.stream(gs):
                 env.step(a1, out=o1)
                 with torch.cuda.graph(graph, stream=gs):
-                    for i in range(TR):
+                    for i in range(GT):
                         env.step(acts[i], out={k: v[i] for k, v in out.items()})
             stream.wait_stream(gs)
             torch.cuda.synchronize(dev)
-            reps = max(1, ks // TR)
+            reps = max(1, ks // GT)
             graph.replay()
             torch.cuda.synchronize(dev)
             ev0.record(stream)
@@ -288,7 +315,7 @@ def run_gpu(args):
                 graph.replay()
             ev1.record(stream)
             torch.cuda.synchronize(dev)
-            graph_ms = ev0.elapsed_time(ev1) / (reps * TR)
+            graph_ms = ev0.elapsed_time(ev1) / (reps * GT)
         except Exception as e:                         # pragma: no cover - reported, not fatal
             print('cuda graph mode failed: %r' % (e,), file=sys.stderr)
 
@@ -310,7 +337,7 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
         e2e = {'value': N * world * ke / float(te_t.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': N * A * 3 * 4, 'd2h_bytes_per_step': N * A * 10 * 4 + N * (4 + 1 + 4),
+               'h2d_bytes_per_step': N * A * 3 * 4, 'd2h_bytes_per_step': N * A * 10 * 4 * (2 if RAW else 1) + N * (4 + 1 + 4),
                'steps': ke, 'rollout_steps_per_call': te,
                'api': 'BatchedAtcEnv.rollout_pinned -> atc_rollout_host (pinned H2D, kernel, D2H, sync)'}
 
@@ -319,11 +346,11 @@ def run_gpu(args):
     peak, peak_src = measured_peaks()
     # dominant kernel = atc_step_kernel<4,...> in rollout mode; the timed region contains nothing else on its stream
     avg_launch_s = ms * 1e-3 / launches
-    bytes_per_launch = bytes_rollout(A, TR) * N * (args.steps / launches)
+    bytes_per_launch = bytes_rollout(A, TR, RAW) * N * (args.steps / launches)
     achieved = bytes_per_launch / avg_launch_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': None, 'peak_source': peak_src, 'kernel': 'atc_rollout_pipe_kernel<4,false,false,false> (rollout, T=%d)' % TR,
-                'algorithmic_bytes_per_env_step': bytes_rollout(A, TR), 'avg_launch_ms': avg_launch_s * 1e3}
+                'algorithmic_bytes_per_env_step': bytes_rollout(A, TR, RAW), 'avg_launch_ms': avg_launch_s * 1e3}
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
         try:
@@ -342,29 +369,52 @@ def run_gpu(args):
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(gpu_launches), 'clocks': clocks,
         'single_step_launch': None if step_ms is None else {
             'ms_per_step': step_ms, 'value': N / (step_ms * 1e-3), 'unit': UNIT,
-            'roofline_frac': bytes_single_step(A) * N / (step_ms * 1e-3) / 1e9 / peak,
+            'roofline_frac': bytes_single_step(A, RAW) * N / (step_ms * 1e-3) / 1e9 / peak,
             'cuda_graph_ms_per_step': graph_ms,
             'cuda_graph_value': None if graph_ms is None else N / (graph_ms * 1e-3),
             'cuda_graph_roofline_frac': None if graph_ms is None else
-            bytes_single_step(A) * N / (graph_ms * 1e-3) / 1e9 / peak},
-        'nccl_gathers': gather.calls,
+            bytes_single_step(A, RAW) * N / (graph_ms * 1e-3) / 1e9 / peak},
+        'nccl_gathers': gather.calls, 'ms_per_rank': ms_ranks,
+        'clocks_per_rank': clocks_ranks if world > 1 else None,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else libraries print to fd 1 (e.g. NCCL's version banner)
+    has been rerouted to stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=65536)
     ap.add_argument('--warmup', type=int, default=1024)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--rollout', type=int, default=128, help='env steps fused per kernel launch')
+    ap.add_argument('--rollout', type=int, default=1024,
+                    help='env steps fused per kernel launch (1024 = the n_steps of the reference\'s PPO2 runner, '
+                         'learning/atc-gym-stable-baselines.py:109-122)')
     ap.add_argument('--e2e-rollout', type=int, default=128)
     ap.add_argument('--e2e-steps', type=int, default=2048)
     ap.add_argument('--cpu-seconds', type=float, default=10.0)
     ap.add_argument('--grid-cell', type=float, default=0.0625, help='MVA lookup grid cell size in nm')
+    ap.add_argument('--raw-obs', type=int, default=1,
+                    help='1: every step also writes info["original_state"] (the raw observation the reference '
+                         'returns, atc_gym.py:192); 0: normalised observation only')
+    ap.add_argument('--gather-overlap', type=int, default=-1,
+                    help='episode-return gather on a side stream (1) or in order on the step stream (0); -1 = default')
     ap.add_argument('--skip-extras', action='store_true', help='only the device-resident timing (used under ncu)')
     args = ap.parse_args()
     if args.warmup < 3:
