@@ -324,6 +324,9 @@ def run_gpu(args):
     if not args.skip_extras:
         te = min(args.e2e_rollout, TR)
         h_act, h_out = env.alloc_pinned_io(te)
+        # what travels back per step: obs, reward, done, term.  info["original_state"] is still written by the kernel,
+        # it stays in HBM (the reference hands it out by reference, too: atc_gym.py:192)
+        h_out = {k: v for k, v in h_out.items() if k != 'raw_obs'}
         h_act.copy_(acts[:te].cpu())
         ke = max(te, (min(args.steps, args.e2e_steps) // te) * te)
         env.rollout_pinned(h_act, h_out)
@@ -337,9 +340,10 @@ def run_gpu(args):
         if world > 1:
             dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
         e2e = {'value': N * world * ke / float(te_t.item()), 'unit': UNIT,
-               'h2d_bytes_per_step': N * A * 3 * 4, 'd2h_bytes_per_step': N * A * 10 * 4 * (2 if RAW else 1) + N * (4 + 1 + 4),
+               'h2d_bytes_per_step': N * A * 3 * 4, 'd2h_bytes_per_step': N * A * 10 * 4 + N * (4 + 1 + 4),
                'steps': ke, 'rollout_steps_per_call': te,
-               'api': 'BatchedAtcEnv.rollout_pinned -> atc_rollout_host (pinned H2D, kernel, D2H, sync)'}
+               'api': 'BatchedAtcEnv.rollout_pinned -> atc_rollout_host (pinned H2D of the actions, kernel, D2H of obs + '
+                      'reward + done + term, sync); info[original_state] stays on the device'}
 
     if rank != 0:
         return
