@@ -19,7 +19,7 @@ OBS_DIM = 10
 
 EXPORTS = ['atc_abi_version', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
            'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
-           'atc_obs_stats_update', 'atc_obs_normalize']
+           'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render']
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -116,6 +116,8 @@ def lib():
     L.atc_obs_normalize.argtypes = [vp, C.c_int64, C.c_int32, vp, C.c_double, C.c_double, vp, vp]
     L.atc_obs_stats_update.restype = C.c_int
     L.atc_obs_normalize.restype = C.c_int
+    L.atc_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]
+    L.atc_render.restype = C.c_int
     L.atc_launch_count.argtypes = [vp]
     L.atc_launch_count.restype = C.c_int64
     L.atc_last_error.argtypes = [vp]

@@ -379,8 +379,14 @@ class BatchedAtcEnv(object):
             nat.check(self._handle, nat.lib().atc_query_corridor(self._handle, q.shape[0], _ptr(q), _ptr(out), self._stream()))
         return out.bool()
 
-    def render(self, mode='human'):
-        raise NotImplementedError("rendering is out of scope (SURVEY.md §2 row 7)")
+    def render(self, mode='rgb_array', env_index=0, trail_xy=None):
+        """AtcGym.render (atc_gym.py:367-552) for one env of the batch, headless: mode 'rgb_array' returns a numpy
+        uint8 image [H, W, 3] drawn by a CUDA kernel (render.py; no text labels).  There is no window system here:
+        mode 'human' raises."""
+        if mode != 'rgb_array':
+            raise NotImplementedError("only mode='rgb_array' is available (headless; SURVEY.md §2 row 7, §8f rank 4)")
+        from .render import render_rgb
+        return render_rgb(self, env_index, trail_xy).cpu().numpy()
 
 
 class AtcGym(object):
@@ -406,10 +412,12 @@ class AtcGym(object):
         self.done = False
         self.last_reward = 0
         self.state = self._env.reset().cpu().numpy().reshape(10)
+        self._history = []                               # Airplane.position_history (model.py:51), render only
         return self.state
 
     def step(self, action):
         a = np.asarray(action, dtype=np.float32).reshape(1, 1, 3)
+        self._history.append((float(self.state[0]), float(self.state[1])))     # model.py:123
         obs, reward, done, info = self._env.step(a)
         self.state = info['original_state'].reshape(10)
         self.done = bool(done[0])
@@ -437,6 +445,10 @@ class AtcGym(object):
         return float(self._env.winning_ratio[0])
 
     def render(self, mode='human'):
+        if mode == 'rgb_array':                          # trail: every 5th of the last 25 positions (atc_gym.py:440-447)
+            n = len(self._history)
+            idx = [i for i in range(n - 5, max(0, n - 25), -1) if i % 5 == 0]
+            return self._env.render(mode, 0, np.asarray([self._history[i] for i in idx], np.float64).reshape(-1, 2))
         return self._env.render(mode)
 
     def close(self):

@@ -193,6 +193,14 @@ int atc_obs_stats_update(const float *x, int64_t n_rows, int32_t dim, double *rm
 int atc_obs_normalize(const float *x, int64_t n_rows, int32_t dim, const double *rms, double epsilon, double clip,
                       float *out, void *stream);
 
+/* Next-row component: headless replacement of AtcGym.render(mode='rgb_array')
+ * (/root/reference/envs/atc/atc_gym.py:367-552, themes.py) — same layout (10 px padding around the sector bbox, scale
+ * from the width; pass height = (int)((bbox_y1 - bbox_y0) * scale) + 20 for the reference's aspect), same elements and
+ * colours, no text labels.  rgb: device uint8 [height][width][3], row 0 = north.  trail_xy: device double [n_trail][2]
+ * past positions drawn as dots; heads_xy: device double [n_heads][2] current aircraft positions drawn as symbols. */
+int atc_render(AtcHandle *h, uint8_t *rgb, int width, int height, const double *trail_xy, int n_trail,
+               const double *heads_xy, int n_heads, void *stream);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t atc_launch_count(const AtcHandle *h);
 const char *atc_last_error(const AtcHandle *h);   /* h may be NULL: last atc_create error */

@@ -1,0 +1,97 @@
+"""Headless renderer: layout helpers on the CPU; the CUDA image against a numpy restatement of
+the picture's geometry (reference: /root/reference/envs/atc/atc_gym.py:367-552, themes.py)."""
+import numpy as np
+import pytest
+import torch
+
+INACTIVE, ACTIVE, LINES, PLANE = (29, 69, 76), (84, 121, 128), (69, 173, 168), (157, 224, 173)      # themes.py x 256
+
+
+def _sector():
+    from atc_reinforcement_learning_b200 import LOWW
+    from atc_reinforcement_learning_b200.sector import CompiledSector
+    return CompiledSector(LOWW(random_entrypoints=True), cell=0.25)
+
+
+def test_image_size_is_the_reference_viewers():
+    from atc_reinforcement_learning_b200.render import image_size
+    cs = _sector()
+    bx0, by0, bx1, by1 = cs.bbox
+    scale = 600 / (bx1 - bx0)                                        # atc_gym.py:376-380
+    assert image_size(cs) == (600 + 20, int((by1 - by0) * scale) + 20)
+
+
+def test_trail_selection_follows_the_reference_loop():
+    from atc_reinforcement_learning_b200.render import trail_from_original_state
+    T = 47
+    raw = torch.zeros(T, 3, 1, 10)
+    raw[:, 1, 0, 0] = torch.arange(T, dtype=torch.float32)           # x = step index
+    got = trail_from_original_state(raw, env_index=1)[:, 0].tolist()
+    n = T
+    exp = [float(i) for i in range(n - 5, max(0, n - 25), -1) if i % 5 == 0]       # atc_gym.py:440-447
+    assert got == exp and len(exp) == 4
+    assert trail_from_original_state(raw[:3], 1).shape == (0, 2)
+
+
+@pytest.mark.gpu
+def test_rendered_image_matches_the_geometry():
+    from atc_reinforcement_learning_b200 import BatchedAtcEnv, LOWW, SimParameters
+    from atc_reinforcement_learning_b200.render import image_size
+    env = BatchedAtcEnv(4, 2, SimParameters(1), LOWW(random_entrypoints=True), seed=3)
+    cs = env.sector
+    trail = np.array([[30.0, 30.0], [31.0, 31.5]])
+    img = env.render('rgb_array', env_index=2, trail_xy=trail)
+    W, H = image_size(cs)
+    assert img.shape == (H, W, 3) and img.dtype == np.uint8
+    scale = 600 / (cs.bbox[2] - cs.bbox[0])
+    colours = {tuple(c) for c in img.reshape(-1, 3)[::7].tolist()}
+    assert colours <= {INACTIVE, ACTIVE, LINES, PLANE} and {INACTIVE, ACTIVE, LINES} <= colours
+
+    def to_screen(x, y):                                             # atc_gym.py:543-552 + padding; row 0 = north
+        return (x - cs.bbox[0]) * scale + 10, (y - cs.bbox[1]) * scale + 10
+
+    def pixel(su, sv):
+        return tuple(img[H - 1 - int(sv), int(su)].tolist())
+
+    # fill: every pixel that is not a line / aircraft pixel is ACTIVE exactly where the reference scan finds an MVA
+    pu, pr = np.meshgrid(np.arange(W), np.arange(H))
+    wx = cs.bbox[0] + (pu + 0.5 - 10) / scale
+    wy = cs.bbox[1] + ((H - 1 - pr) + 0.5 - 10) / scale
+    inside = cs.find_mva_np(wx.ravel(), wy.ravel()).reshape(H, W) >= 0
+    is_fill = np.all(img == np.array(ACTIVE, np.uint8), -1) | np.all(img == np.array(INACTIVE, np.uint8), -1)
+    assert is_fill.mean() > 0.9
+    np.testing.assert_array_equal(np.all(img == np.array(ACTIVE, np.uint8), -1)[is_fill], inside[is_fill])
+    # runway centre, the FAF symbol's top corner and a drawn dash of the approach line are line pixels
+    assert pixel(*to_screen(*cs.runway[:2])) == LINES
+    fu, fv = to_screen(*cs.faf)
+    assert pixel(fu, fv + 6) == LINES
+    (rx, ry), (ix, iy) = cs.runway[:2], cs.iaf
+    t = 0.5 / 48                                                     # middle of the first (drawn) segment
+    assert pixel(*to_screen(rx + t * (ix - rx), ry + t * (iy - ry))) == LINES
+    t = 1.5 / 48                                                     # middle of the first gap ... unless an MVA edge runs there
+    assert pixel(*to_screen(rx + t * (ix - rx), ry + t * (iy - ry))) in (ACTIVE, INACTIVE, LINES)
+    # the env's two aircraft: square outline 1.8 .. 3.8 px around the position, hollow centre; trail dots are filled
+    st, _ = env.get_state()
+    for a in range(2):
+        su, sv = to_screen(float(st[2, a, 0]), float(st[2, a, 1]))
+        assert pixel(su + 2.9, sv) == PLANE and pixel(su, sv - 2.9) == PLANE
+        assert pixel(su, sv) != PLANE
+    for x, y in trail:
+        assert pixel(*to_screen(x, y)) == PLANE
+    with pytest.raises(NotImplementedError):
+        env.render('human')
+    with pytest.raises(IndexError):
+        env.render('rgb_array', env_index=4)
+
+
+@pytest.mark.gpu
+def test_adaptor_renders_its_own_trail():
+    from atc_reinforcement_learning_b200 import make
+    env = make('AtcEnv-v0')
+    env.reset()
+    for _ in range(40):
+        env.step(np.array([0.0, 0.5, 0.2], np.float32))
+    img = env.render('rgb_array')
+    plane = np.all(img == np.array(PLANE, np.uint8), -1)
+    assert plane.sum() > 30                                          # symbol outline + 4 trail dots
+    env.close()
