@@ -13,11 +13,11 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libatc_b200.so')
 INCLUDE = os.path.join(ROOT, 'include')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_AIRCRAFT = 8
 OBS_DIM = 10
 
-EXPORTS = ['atc_abi_version', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
+EXPORTS = ['atc_abi_version', 'atc_compact_grid_budget', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
            'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
            'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render']
 
@@ -42,6 +42,9 @@ class AtcSectorDesc(C.Structure):
         ('grid_cell', C.POINTER(C.c_uint16)), ('n_mixed', C.c_int32), ('n_prog', C.c_int32),
         ('grid_prog_off', C.POINTER(C.c_uint32)), ('grid_prog', C.POINTER(C.c_uint16)), ('grid_line', _dp),
         ('wind_gx', C.c_int32), ('wind_gy', C.c_int32), ('wind', _fp),
+        ('cgrid_nx', C.c_int32), ('cgrid_ny', C.c_int32), ('cgrid_inv_cell', C.c_double),
+        ('cgrid_x0', C.c_double), ('cgrid_y0', C.c_double), ('cgrid_cell', C.POINTER(C.c_uint16)),
+        ('n_cline', C.c_int32), ('cline', _dp),
     ]
 
 
@@ -118,6 +121,8 @@ def lib():
     L.atc_obs_normalize.restype = C.c_int
     L.atc_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]
     L.atc_render.restype = C.c_int
+    L.atc_compact_grid_budget.argtypes = []
+    L.atc_compact_grid_budget.restype = C.c_int64
     L.atc_launch_count.argtypes = [vp]
     L.atc_launch_count.restype = C.c_int64
     L.atc_last_error.argtypes = [vp]
@@ -163,6 +168,12 @@ def sector_desc(cs):
     if cs.wind is not None:
         d.wind_gy, d.wind_gx = cs.wind.shape[0], cs.wind.shape[1]
         d.wind = _np_ptr(cs.wind, C.c_float)
+    cg = getattr(cs, 'compact', None)
+    if cg is not None:
+        d.cgrid_nx, d.cgrid_ny, d.cgrid_inv_cell = cg.grid_nx, cg.grid_ny, cg.grid_inv_cell
+        d.cgrid_x0, d.cgrid_y0 = cg.grid_x0, cg.grid_y0
+        d.cgrid_cell = _np_ptr(cg.grid_cell, C.c_uint16)
+        d.n_cline, d.cline = cg.n_lines, _np_ptr(cg.lines, C.c_double)
     return d
 
 

@@ -9,6 +9,7 @@ include/atc_b200.h.  PyTorch owns every device tensor; the kernels live in csrc/
 
 `AtcGym` is the call-compatible single-env adaptor (N = 1, one aircraft, numpy in / numpy out, no auto-reset).
 """
+import copy
 import ctypes as C
 
 import numpy as np
@@ -61,7 +62,7 @@ class BatchedAtcEnv(object):
 
     def __init__(self, num_envs, num_aircraft=1, sim_parameters=None, scenario=None, device='cuda:0', seed=0,
                  wind=None, autoreset=True, track_actions=False, return_raw_obs=True, normalize_reset_obs=False,
-                 env_index_base=0, grid_cell=0.0625, exact_math=False):
+                 env_index_base=0, grid_cell=0.0625, exact_math=False, compact_grid=True):
         self._handle = None
         if sim_parameters is None:
             sim_parameters = model.SimParameters(1)
@@ -80,6 +81,13 @@ class BatchedAtcEnv(object):
         self._sim_parameters = sim_parameters
         self._scenario = scenario
         self.sector = compile_sector_cached(scenario, grid_cell, wind)
+        if compact_grid and not hasattr(self.sector, 'compact'):
+            # coarse copy of the MVA grid for the shared memory of one SM (sector.CompactGrid); None if it cannot be built
+            from .sector import build_compact_grid
+            self.sector.compact = build_compact_grid(scenario, int(nat.lib().atc_compact_grid_budget()))
+        elif not compact_grid:
+            self.sector = copy.copy(self.sector)
+            self.sector.compact = None
         self.autoreset = bool(autoreset)
         self.track_actions = bool(track_actions)
         self.return_raw_obs = bool(return_raw_obs)

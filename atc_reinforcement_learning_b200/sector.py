@@ -361,3 +361,108 @@ class CompiledSector(object):
                     out[i] = m
                     break
         return out
+
+
+# ------------------------------------------------------------------------------------------------ compact (shared-memory) grid
+COMPACT_ESCAPE = 127          # line id meaning "not decidable here": take the fine grid
+COMPACT_MAX_LINES = 127
+COMPACT_MAX_ANSWER = 15       # polygon index + 1 must fit four bits
+
+
+class CompactGrid(object):
+    """A second, coarse MVA grid small enough for the shared memory of one SM: the rollout kernel
+    with one CTA per SM keeps it next to its message rings, so the per-step lookup is a shared-memory load instead of
+    an L2 round trip.  Built from the same exact machinery as the fine grid (a CompiledSector at the coarse cell):
+
+      cell (u16)  bit 15 clear: polygon index + 1 of the whole (margin-grown) cell, 0 = outside
+                  bit 15 set  : bits 0-6 line id, bits 7-10 answer on the positive side, bits 11-14 on the negative
+                                side (polygon index + 1) of the ONE boundary line that crosses the cell;
+                                line id 127: undecidable here
+      lines (f64) [n_lines][4]: a, b, c (a*a + b*b = 1), 0 — deduplicated over the cells
+
+    A point farther than LINE_EPS from its cell's line takes that side's answer; everything else (line id 127, within
+    LINE_EPS of the line) is resolved by the fine grid, which is exact everywhere.  Only sectors with at most 127
+    distinct boundary lines and 15 polygons get a compact grid (LOWW: 12 polygons, < 127 lines)."""
+
+    def __init__(self, scenario, cell, wind=None):
+        cs = CompiledSector(scenario, cell=cell, wind=None)
+        self.cell, self.margin = cs.cell, cs.margin
+        self.grid_nx, self.grid_ny = cs.grid_nx, cs.grid_ny
+        self.grid_x0, self.grid_y0, self.grid_inv_cell = cs.grid_x0, cs.grid_y0, cs.grid_inv_cell
+        self._cs = cs
+        g = cs.grid_cell
+        out = np.where((g & 0x8000) == 0, g, np.uint16(0x8000 | COMPACT_ESCAPE)).astype(np.uint16)
+        rec = cs.grid_line
+        rec_out = rec.view(np.int32).reshape(-1, 8)
+        lines, index = [], {}
+        iys, ixs = np.nonzero((g & 0x8000) != 0)
+        n_line_cells = 0
+        for iy, ix in zip(iys.tolist(), ixs.tolist()):
+            k = int(g[iy, ix]) & 0x7FFF
+            a, b, c = (float(v) for v in rec[k, :3])
+            if a == 0.0 and b == 0.0:
+                continue
+            pos, neg = int(rec_out[k, 6]), int(rec_out[k, 7])
+            if not (0 <= pos <= COMPACT_MAX_ANSWER and 0 <= neg <= COMPACT_MAX_ANSWER):
+                continue
+            key = (a, b, c)
+            lid = index.get(key)
+            if lid is None:
+                if len(lines) >= COMPACT_MAX_LINES:
+                    continue                                          # table full: the cell stays undecidable
+                lid = index[key] = len(lines)
+                lines.append((a, b, c, 0.0))
+            out[iy, ix] = 0x8000 | lid | (pos << 7) | (neg << 11)
+            n_line_cells += 1
+        self.grid_cell = np.ascontiguousarray(out)
+        self.lines = np.ascontiguousarray(lines if lines else [(0.0, 0.0, 0.0, 0.0)], np.float64)
+        self.n_lines = len(lines)
+        self.mixed_fraction = float(((out & 0x8000) != 0).mean())
+        self.escape_fraction = float((out == (0x8000 | COMPACT_ESCAPE)).mean())
+        self.nbytes = int(self.grid_cell.nbytes + self.lines.nbytes)
+
+    def cell_index_np(self, x, y):
+        return self._cs.cell_index_np(x, y)
+
+    def lookup_np(self, x, y, fine, cells=None):
+        """Host restatement of the kernel's shared-memory lookup; `fine` is the CompiledSector whose exact lookup
+        resolves the undecidable points.  Returns (polygon index or -1, mask of the points the fine grid resolved)."""
+        x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+        ix, iy = self.cell_index_np(x, y) if cells is None else cells
+        cell = self.grid_cell[iy, ix].astype(np.int64)
+        out = np.where((cell & 0x8000) == 0, cell - 1, -2)
+        mixed = (cell & 0x8000) != 0
+        lid = cell & 127
+        has_line = mixed & (lid != COMPACT_ESCAPE)
+        ln = self.lines[np.where(has_line, lid, 0)]
+        # the kernel's evaluation order: fma(a, x, fma(b, y, c)) — numpy has no FMA; the sign test only needs |d| > eps,
+        # and d is compared against LINE_EPS = 1e-9 >> the rounding of either order
+        d = ln[:, 0] * x + (ln[:, 1] * y + ln[:, 2])
+        out = np.where(has_line & (d > LINE_EPS), ((cell >> 7) & 15) - 1, out)
+        out = np.where(has_line & (d < -LINE_EPS), ((cell >> 11) & 15) - 1, out)
+        slow = out == -2
+        if slow.any():
+            out = out.copy()
+            out[slow] = fine.lookup_np(x[slow], y[slow])
+        return out.astype(np.int32), slow
+
+
+def build_compact_grid(scenario, budget_bytes, cells=(0.25, 0.3, 0.35, 0.4, 0.5, 0.6, 0.75, 1.0)):
+    """The finest CompactGrid of `cells` that fits `budget_bytes`, or None (too many polygons, or nothing fits)."""
+    if len(scenario.mvas) > COMPACT_MAX_ANSWER:
+        return None
+    for c in cells:
+        b = CompiledSector.__new__(CompiledSector)      # bbox only: a cheap size estimate before the real build
+        rings = [np.asarray(m.area_as_list, np.float64) for m in scenario.mvas]
+        xs = np.concatenate([r[:, 0] for r in rings]); ys = np.concatenate([r[:, 1] for r in rings])
+        nx = int(math.floor((xs.max() - xs.min()) / c)) + 2 + 2 * GRID_PAD
+        ny = int(math.floor((ys.max() - ys.min()) / c)) + 2 + 2 * GRID_PAD
+        if nx * ny * 2 + 32 * COMPACT_MAX_LINES > budget_bytes:
+            continue
+        try:
+            g = CompactGrid(scenario, c)
+        except ValueError:
+            continue
+        if g.nbytes <= budget_bytes:
+            return g
+    return None

@@ -350,11 +350,12 @@ def run_gpu(args):
     peak, peak_src = measured_peaks()
     # dominant kernel = atc_step_kernel<4,...> in rollout mode; the timed region contains nothing else on its stream
     avg_launch_s = ms * 1e-3 / launches
-    bytes_per_launch = bytes_rollout(A, TR, RAW) * N * (args.steps / launches)
+    t_launch = args.steps / launches                    # mean steps per launch (the last launch may be shorter)
+    bytes_per_launch = bytes_rollout(A, t_launch, RAW) * N * t_launch
     achieved = bytes_per_launch / avg_launch_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': None, 'peak_source': peak_src, 'kernel': 'atc_rollout_pipe_kernel<4,false,false,false> (rollout, T=%d)' % TR,
-                'algorithmic_bytes_per_env_step': bytes_rollout(A, TR, RAW), 'avg_launch_ms': avg_launch_s * 1e3}
+                'algorithmic_bytes_per_env_step': bytes_rollout(A, t_launch, RAW), 'avg_launch_ms': avg_launch_s * 1e3}
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
         try:

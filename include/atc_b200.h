@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ATC_ABI_VERSION 2
+#define ATC_ABI_VERSION 3
 #define ATC_MAX_AIRCRAFT 8
 #define ATC_MAX_MVA 31
 #define ATC_OBS_DIM 10
@@ -103,6 +103,18 @@ typedef struct AtcSectorDesc {
     /* wind extension (not in the reference; README.md:64) — NULL / 0 = calm */
     int32_t wind_gx, wind_gy;
     const float *wind;             /* [wind_gy][wind_gx][2] knots (east, north), nodes on the bbox corners */
+    /* optional compact grid, NULL = none: a coarse copy of the accelerator small enough to live in
+       the shared memory of one SM (at most atc_compact_grid_budget() bytes for cells + lines); the rollout kernel
+       with one CTA per SM reads it instead of the fine grid.  Same geometry conventions as the fine grid.
+       cell: bit 15 clear = polygon + 1 for the whole cell (0 = outside); bit 15 set = bits 0-6 line id (127: undecidable
+       here), bits 7-10 / 11-14 answer (polygon + 1) on the positive / negative side of that line.  Points within 1e-9
+       nm of the line and undecidable cells are resolved through the fine grid. */
+    int32_t cgrid_nx, cgrid_ny;
+    double cgrid_inv_cell;
+    double cgrid_x0, cgrid_y0;
+    const uint16_t *cgrid_cell;    /* [cgrid_ny][cgrid_nx] */
+    int32_t n_cline;               /* <= 127 */
+    const double *cline;           /* [n_cline][4]: a, b, c (a*a + b*b = 1), 0 */
 } AtcSectorDesc;
 
 /* model.py:132-145 SimParameters + batch geometry */
@@ -147,6 +159,9 @@ typedef struct AtcStepIO {
 typedef struct AtcHandle AtcHandle;
 
 int atc_abi_version(void);
+
+/* Bytes of shared memory the one-CTA-per-SM rollout kernel can give to a compact grid (cells + lines). */
+int64_t atc_compact_grid_budget(void);
 
 /* Replaces AtcGym.__init__ (atc_gym.py:28-115) for a batch: validates, copies the sector to `device`. */
 int atc_create(const AtcSectorDesc *sector, const AtcSimParams *params, int device, AtcHandle **out);

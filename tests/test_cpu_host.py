@@ -299,3 +299,53 @@ def test_oracle_autoreset_and_metrics():
         ts = np.nonzero(done[:, e])[0]
         np.testing.assert_allclose(m['last_ep_return'][e], rew[ts[-2] + 1:ts[-1] + 1, e].sum(), rtol=1e-12)
         assert m['last_ep_len'][e] == ts[-1] - ts[-2]
+
+
+@pytest.mark.parametrize('scn', ['LOWW', 'SimpleScenario'])
+def test_compact_grid_is_exact(scn):
+    """sector.CompactGrid (the coarse copy of the MVA accelerator the one-CTA-per-SM rollout kernel keeps in shared
+    memory): its lookup + fine-grid fallback equals the reference scan on random, on-edge, near-vertex and
+    cell-border points, for the point's own cell and for every neighbour within the float32 margin."""
+    import atc_reinforcement_learning_b200 as P
+    from atc_reinforcement_learning_b200 import _native as nat
+    from atc_reinforcement_learning_b200.sector import CompiledSector, build_compact_grid
+    s = getattr(P, scn)(random_entrypoints=(scn == 'LOWW'))
+    fine = CompiledSector(s, cell=0.25)
+    budget = int(nat.lib().atc_compact_grid_budget())
+    assert 100 * 1024 < budget < 227 * 1024
+    cg = build_compact_grid(s, budget)
+    assert cg is not None and cg.nbytes <= budget and cg.n_lines <= 127
+    assert build_compact_grid(s, 1024) is None                      # nothing fits
+    rng = np.random.RandomState(4)
+    b = fine.bbox
+    n = 200000
+    xs = [rng.uniform(b[0] - 2, b[2] + 2, n)]; ys = [rng.uniform(b[1] - 2, b[3] + 2, n)]
+    for ring in fine.rings:                                          # on / next to the edges and vertices
+        for i in range(1, len(ring)):
+            t = rng.uniform(0, 1, 200)
+            ex = ring[i - 1][0] + t * (ring[i][0] - ring[i - 1][0]); ey = ring[i - 1][1] + t * (ring[i][1] - ring[i - 1][1])
+            for d in (0.0, 1e-12, -1e-12, 1e-9, -1e-9, 3e-9, -3e-9, 1e-6, -1e-6, 1e-3):
+                xs.append(ex + d); ys.append(ey - d)
+    k = rng.randint(0, cg.grid_nx, 20000); l = rng.randint(0, cg.grid_ny, 20000)      # cell borders and corners
+    for d in (0.0, 1e-9, -1e-9, 1e-6, -1e-6):
+        xs.append(cg.grid_x0 + k * cg.cell + d); ys.append(cg.grid_y0 + l * cg.cell + rng.uniform(0, cg.cell, 20000))
+        xs.append(cg.grid_x0 + k * cg.cell + d); ys.append(cg.grid_y0 + l * cg.cell - d)
+    x, y = np.concatenate(xs), np.concatenate(ys)
+    ref = fine.find_mva_np(x, y)
+    got, slow = cg.lookup_np(x, y, fine)
+    np.testing.assert_array_equal(got, ref)
+    assert slow.mean() < 0.25                                        # most points never touch the fine grid
+    ix, iy = cg.cell_index_np(x, y)
+    for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):               # a neighbouring cell within the margin: same answer
+        fx = (x - cg.grid_x0) * cg.grid_inv_cell; fy = (y - cg.grid_y0) * cg.grid_inv_cell
+        near = (np.abs(fx - np.round(fx)) * cg.cell < cg.margin) if dx else (np.abs(fy - np.round(fy)) * cg.cell < cg.margin)
+        jx = np.clip(ix + dx, 0, cg.grid_nx - 1); jy = np.clip(iy + dy, 0, cg.grid_ny - 1)
+        tx = np.clip(np.floor(fx + (0.5 if dx > 0 else -0.5) * (dx != 0)), 0, cg.grid_nx - 1).astype(np.int64)
+        sel = near & (np.abs(jx - np.floor(fx)) <= 1) & (np.abs(jy - np.floor(fy)) <= 1) & \
+            ((jx == np.floor(fx)) | (np.abs(fx - np.round(fx)) * cg.cell < cg.margin)) & \
+            ((jy == np.floor(fy)) | (np.abs(fy - np.round(fy)) * cg.cell < cg.margin))
+        sel &= (np.abs((jx + 0.5) - fx) <= 0.5 + cg.margin * cg.grid_inv_cell) & \
+               (np.abs((jy + 0.5) - fy) <= 0.5 + cg.margin * cg.grid_inv_cell)
+        if sel.any():
+            g2, _ = cg.lookup_np(x[sel], y[sel], fine, cells=(jx[sel], jy[sel]))
+            np.testing.assert_array_equal(g2, ref[sel])
