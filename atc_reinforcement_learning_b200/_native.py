@@ -44,7 +44,7 @@ class AtcSectorDesc(C.Structure):
         ('wind_gx', C.c_int32), ('wind_gy', C.c_int32), ('wind', _fp),
         ('cgrid_nx', C.c_int32), ('cgrid_ny', C.c_int32), ('cgrid_inv_cell', C.c_double),
         ('cgrid_x0', C.c_double), ('cgrid_y0', C.c_double), ('cgrid_cell', C.POINTER(C.c_uint16)),
-        ('n_cline', C.c_int32), ('cline', _dp),
+        ('cgrid_n_blocks', C.c_int32), ('n_cline', C.c_int32), ('cline', _dp),
     ]
 
 
@@ -170,9 +170,10 @@ def sector_desc(cs):
         d.wind = _np_ptr(cs.wind, C.c_float)
     cg = getattr(cs, 'compact', None)
     if cg is not None:
-        d.cgrid_nx, d.cgrid_ny, d.cgrid_inv_cell = cg.grid_nx, cg.grid_ny, cg.grid_inv_cell
+        d.cgrid_nx, d.cgrid_ny, d.cgrid_inv_cell = cg.grid_nx, cg.grid_ny, cg.sub_inv_cell
         d.cgrid_x0, d.cgrid_y0 = cg.grid_x0, cg.grid_y0
         d.cgrid_cell = _np_ptr(cg.grid_cell, C.c_uint16)
+        d.cgrid_n_blocks = cg.n_blocks
         d.n_cline, d.cline = cg.n_lines, _np_ptr(cg.lines, C.c_double)
     return d
 

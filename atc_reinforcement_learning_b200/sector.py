@@ -42,7 +42,7 @@ def _rot_apply(phi_deg, vx, vy):
 
 
 class CompiledSector(object):
-    def __init__(self, scenario, cell=0.25, margin=None, wind=None):
+    def __init__(self, scenario, cell=0.25, margin=None, wind=None, grid_origin=None):
         mvas = scenario.mvas
         if len(mvas) > MAX_MVA:
             raise ValueError("at most %d MVA polygons are supported" % MAX_MVA)
@@ -122,6 +122,7 @@ class CompiledSector(object):
             err = 2.0 ** -24 * (float(np.abs(self.bbox).max()) + 2.0 * self.cell * n_cells)
             margin = max(1e-6, 4.0 * err)
         self.margin = float(margin)
+        self.grid_origin = grid_origin
         self._build_grid()
 
     # ---------------------------------------------------------------------------------------------- reference scan
@@ -142,6 +143,10 @@ class CompiledSector(object):
         cs, mg = self.cell, self.margin
         # the grid starts GRID_PAD cells outside the bbox and ends GRID_PAD cells beyond it
         x0, y0 = self.bbox[0] - GRID_PAD * cs, self.bbox[1] - GRID_PAD * cs
+        if self.grid_origin is not None:                # a grid aligned with another one (sector.CompactGrid)
+            if self.grid_origin[0] > x0 or self.grid_origin[1] > y0:
+                raise ValueError("grid_origin must leave GRID_PAD cells outside the bbox")
+            x0, y0 = float(self.grid_origin[0]), float(self.grid_origin[1])
         nx = int(math.floor((self.bbox[2] - x0) / cs)) + 1 + GRID_PAD
         ny = int(math.floor((self.bbox[3] - y0) / cs)) + 1 + GRID_PAD
         self.grid_nx, self.grid_ny = nx, ny
@@ -365,78 +370,124 @@ class CompiledSector(object):
 
 # ------------------------------------------------------------------------------------------------ compact (shared-memory) grid
 COMPACT_ESCAPE = 127          # line id meaning "not decidable here": take the fine grid
-COMPACT_MAX_LINES = 127
+COMPACT_SUB0 = 126            # coarse level only: line ids 126 / 127 = "look in sub-block (id & 1) * 256 + bits 7-14"
+COMPACT_MAX_LINES = 126
 COMPACT_MAX_ANSWER = 15       # polygon index + 1 must fit four bits
+COMPACT_SUB = 8               # a sub-block refines one coarse cell into 8 x 8 cells
+COMPACT_MAX_BLOCKS = 511      # block 511 is the shared "undecidable everywhere" block
+
+
+def _compact_cells(cs, lines, index):
+    """CompiledSector grid -> compact u16 cells (uniform / single-line / 0x8000 | 127), line table shared via `index`."""
+    g = cs.grid_cell
+    out = np.where((g & 0x8000) == 0, g, np.uint16(0x8000 | COMPACT_ESCAPE)).astype(np.uint16)
+    rec = cs.grid_line
+    rec_out = rec.view(np.int32).reshape(-1, 8)
+    iys, ixs = np.nonzero((g & 0x8000) != 0)
+    for iy, ix in zip(iys.tolist(), ixs.tolist()):
+        k = int(g[iy, ix]) & 0x7FFF
+        a, b, c = (float(v) for v in rec[k, :3])
+        if a == 0.0 and b == 0.0:
+            continue
+        pos, neg = int(rec_out[k, 6]), int(rec_out[k, 7])
+        if not (0 <= pos <= COMPACT_MAX_ANSWER and 0 <= neg <= COMPACT_MAX_ANSWER):
+            continue
+        key = (a, b, c)
+        lid = index.get(key)
+        if lid is None:
+            if len(lines) >= COMPACT_MAX_LINES:
+                continue                                          # table full: the cell stays undecidable
+            lid = index[key] = len(lines)
+            lines.append((a, b, c, 0.0))
+        out[iy, ix] = 0x8000 | lid | (pos << 7) | (neg << 11)
+    return out
 
 
 class CompactGrid(object):
     """A second, coarse MVA grid small enough for the shared memory of one SM: the rollout kernel
     with one CTA per SM keeps it next to its message rings, so the per-step lookup is a shared-memory load instead of
-    an L2 round trip.  Built from the same exact machinery as the fine grid (a CompiledSector at the coarse cell):
+    an L2 round trip.  Built from the same exact machinery as the fine grid (CompiledSector at the coarse cell and at
+    1/8 of it, same origin), two levels:
 
-      cell (u16)  bit 15 clear: polygon index + 1 of the whole (margin-grown) cell, 0 = outside
-                  bit 15 set  : bits 0-6 line id, bits 7-10 answer on the positive side, bits 11-14 on the negative
-                                side (polygon index + 1) of the ONE boundary line that crosses the cell;
-                                line id 127: undecidable here
-      lines (f64) [n_lines][4]: a, b, c (a*a + b*b = 1), 0 — deduplicated over the cells
+      coarse cell (u16)  bit 15 clear: polygon index + 1 of the whole (margin-grown) cell, 0 = outside
+                         bit 15 set, line id (bits 0-6) < 126: ONE boundary line crosses the cell; bits 7-10 / 11-14 =
+                                     answer (polygon index + 1) on its positive / negative side
+                         bit 15 set, line id 126 / 127: the cell holds a vertex or several lines; its 8 x 8 sub-block
+                                     number (id & 1) * 256 + bits 7-14 refines it (block 511: nothing decidable)
+      sub-block cells    same encoding at 1/8 of the cell size; line id 127 = undecidable
+      lines (f64)        [n_lines][4]: a, b, c (a*a + b*b = 1), 0 — deduplicated over both levels
 
-    A point farther than LINE_EPS from its cell's line takes that side's answer; everything else (line id 127, within
-    LINE_EPS of the line) is resolved by the fine grid, which is exact everywhere.  Only sectors with at most 127
-    distinct boundary lines and 15 polygons get a compact grid (LOWW: 12 polygons, < 127 lines)."""
+    The index is taken at the sub-cell resolution (float32, like the fine grid's) and shifted down by 3 for the coarse
+    cell.  A point farther than LINE_EPS from its cell's line takes that side's answer; everything undecidable is
+    resolved by the fine grid, which is exact everywhere.  Only sectors with at most 126 distinct boundary lines and 15
+    polygons get a compact grid (LOWW: 12 polygons, 60 lines)."""
 
     def __init__(self, scenario, cell, wind=None):
-        cs = CompiledSector(scenario, cell=cell, wind=None)
+        sub = COMPACT_SUB
+        probe = CompiledSector(scenario, cell=cell)                      # fixes the common origin
+        origin = (probe.grid_x0, probe.grid_y0)
+        fine = CompiledSector(scenario, cell=cell / sub, grid_origin=origin)
+        cs = CompiledSector(scenario, cell=cell, margin=max(probe.margin, fine.margin))
+        assert (cs.grid_x0, cs.grid_y0) == origin
         self.cell, self.margin = cs.cell, cs.margin
         self.grid_nx, self.grid_ny = cs.grid_nx, cs.grid_ny
         self.grid_x0, self.grid_y0, self.grid_inv_cell = cs.grid_x0, cs.grid_y0, cs.grid_inv_cell
-        self._cs = cs
-        g = cs.grid_cell
-        out = np.where((g & 0x8000) == 0, g, np.uint16(0x8000 | COMPACT_ESCAPE)).astype(np.uint16)
-        rec = cs.grid_line
-        rec_out = rec.view(np.int32).reshape(-1, 8)
+        self._fine = fine                                                 # cell_index_np at the sub-cell resolution
+        self.sub_inv_cell = fine.grid_inv_cell
         lines, index = [], {}
-        iys, ixs = np.nonzero((g & 0x8000) != 0)
-        n_line_cells = 0
-        for iy, ix in zip(iys.tolist(), ixs.tolist()):
-            k = int(g[iy, ix]) & 0x7FFF
-            a, b, c = (float(v) for v in rec[k, :3])
-            if a == 0.0 and b == 0.0:
-                continue
-            pos, neg = int(rec_out[k, 6]), int(rec_out[k, 7])
-            if not (0 <= pos <= COMPACT_MAX_ANSWER and 0 <= neg <= COMPACT_MAX_ANSWER):
-                continue
-            key = (a, b, c)
-            lid = index.get(key)
-            if lid is None:
-                if len(lines) >= COMPACT_MAX_LINES:
-                    continue                                          # table full: the cell stays undecidable
-                lid = index[key] = len(lines)
-                lines.append((a, b, c, 0.0))
-            out[iy, ix] = 0x8000 | lid | (pos << 7) | (neg << 11)
-            n_line_cells += 1
-        self.grid_cell = np.ascontiguousarray(out)
+        coarse = _compact_cells(cs, lines, index)
+        fcells = _compact_cells(fine, lines, index)
+        ny, nx = coarse.shape
+        pad = np.zeros((ny * sub, nx * sub), np.uint16)                   # beyond the fine grid: outside
+        fy, fx = min(pad.shape[0], fcells.shape[0]), min(pad.shape[1], fcells.shape[1])
+        pad[:fy, :fx] = fcells[:fy, :fx]
+        blocks = []
+        for iy, ix in zip(*[v.tolist() for v in np.nonzero(coarse == (0x8000 | COMPACT_ESCAPE))]):
+            j = len(blocks)
+            if j >= COMPACT_MAX_BLOCKS:
+                j = COMPACT_MAX_BLOCKS
+            else:
+                blocks.append(pad[iy * sub:(iy + 1) * sub, ix * sub:(ix + 1) * sub].reshape(-1))
+            coarse[iy, ix] = 0x8000 | (COMPACT_SUB0 + (j >> 8)) | ((j & 255) << 7)
+        self.n_blocks = len(blocks)
+        self.n_coarse = nx * ny
+        flat = [coarse.reshape(-1)] + blocks
+        self.grid_cell = np.ascontiguousarray(np.concatenate(flat).astype(np.uint16))
+        self.coarse = coarse
         self.lines = np.ascontiguousarray(lines if lines else [(0.0, 0.0, 0.0, 0.0)], np.float64)
         self.n_lines = len(lines)
-        self.mixed_fraction = float(((out & 0x8000) != 0).mean())
-        self.escape_fraction = float((out == (0x8000 | COMPACT_ESCAPE)).mean())
+        self.mixed_fraction = float(((coarse & 0x8000) != 0).mean())
+        self.block_fraction = float((((coarse & 0x8000) != 0) & ((coarse & 127) >= COMPACT_SUB0)).mean())
+        sub_esc = sum(int((b == (0x8000 | COMPACT_ESCAPE)).sum()) for b in blocks)
+        self.escape_fraction = sub_esc / float(sub * sub * max(self.n_coarse, 1))      # area that needs the fine grid
         self.nbytes = int(self.grid_cell.nbytes + self.lines.nbytes)
 
     def cell_index_np(self, x, y):
-        return self._cs.cell_index_np(x, y)
+        """(ix8, iy8): the kernel's float32 index at the sub-cell resolution, clamped to the compact grid."""
+        ix8, iy8 = self._fine.cell_index_np(x, y)
+        return (np.minimum(ix8, self.grid_nx * COMPACT_SUB - 1), np.minimum(iy8, self.grid_ny * COMPACT_SUB - 1))
 
     def lookup_np(self, x, y, fine, cells=None):
         """Host restatement of the kernel's shared-memory lookup; `fine` is the CompiledSector whose exact lookup
-        resolves the undecidable points.  Returns (polygon index or -1, mask of the points the fine grid resolved)."""
+        resolves the undecidable points; `cells` = (ix8, iy8) overrides the index.  Returns (polygon index or -1, mask
+        of the points the fine grid resolved)."""
         x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
-        ix, iy = self.cell_index_np(x, y) if cells is None else cells
-        cell = self.grid_cell[iy, ix].astype(np.int64)
+        ix8, iy8 = self.cell_index_np(x, y) if cells is None else cells
+        g = self.grid_cell.astype(np.int64)
+        cell = g[(iy8 >> 3) * self.grid_nx + (ix8 >> 3)]
+        is_blk = ((cell & 0x8000) != 0) & ((cell & 127) >= COMPACT_SUB0)
+        j = ((cell & 1) << 8) | ((cell >> 7) & 255)
+        j = np.where(is_blk & (j < self.n_blocks), j, 0)
+        sub_cell = g[np.minimum(self.n_coarse + 64 * j + ((iy8 & 7) << 3) + (ix8 & 7), len(g) - 1)] if self.n_blocks else cell
+        undecidable_blk = is_blk & ((((cell & 1) << 8) | ((cell >> 7) & 255)) >= self.n_blocks)
+        cell = np.where(is_blk, sub_cell, cell)
         out = np.where((cell & 0x8000) == 0, cell - 1, -2)
-        mixed = (cell & 0x8000) != 0
         lid = cell & 127
-        has_line = mixed & (lid != COMPACT_ESCAPE)
+        has_line = ((cell & 0x8000) != 0) & (lid < COMPACT_SUB0) & ~undecidable_blk
+        out = np.where(undecidable_blk, -2, out)
         ln = self.lines[np.where(has_line, lid, 0)]
-        # the kernel's evaluation order: fma(a, x, fma(b, y, c)) — numpy has no FMA; the sign test only needs |d| > eps,
-        # and d is compared against LINE_EPS = 1e-9 >> the rounding of either order
+        # the kernel evaluates fma(a, x, fma(b, y, c)); numpy has no FMA, but d is only compared against
+        # LINE_EPS = 1e-9, far above the rounding of either order
         d = ln[:, 0] * x + (ln[:, 1] * y + ln[:, 2])
         out = np.where(has_line & (d > LINE_EPS), ((cell >> 7) & 15) - 1, out)
         out = np.where(has_line & (d < -LINE_EPS), ((cell >> 11) & 15) - 1, out)
@@ -451,13 +502,12 @@ def build_compact_grid(scenario, budget_bytes, cells=(0.25, 0.3, 0.35, 0.4, 0.5,
     """The finest CompactGrid of `cells` that fits `budget_bytes`, or None (too many polygons, or nothing fits)."""
     if len(scenario.mvas) > COMPACT_MAX_ANSWER:
         return None
+    rings = [np.asarray(m.area_as_list, np.float64) for m in scenario.mvas]
+    xs = np.concatenate([r[:, 0] for r in rings]); ys = np.concatenate([r[:, 1] for r in rings])
     for c in cells:
-        b = CompiledSector.__new__(CompiledSector)      # bbox only: a cheap size estimate before the real build
-        rings = [np.asarray(m.area_as_list, np.float64) for m in scenario.mvas]
-        xs = np.concatenate([r[:, 0] for r in rings]); ys = np.concatenate([r[:, 1] for r in rings])
-        nx = int(math.floor((xs.max() - xs.min()) / c)) + 2 + 2 * GRID_PAD
+        nx = int(math.floor((xs.max() - xs.min()) / c)) + 2 + 2 * GRID_PAD      # a cheap size estimate before the build
         ny = int(math.floor((ys.max() - ys.min()) / c)) + 2 + 2 * GRID_PAD
-        if nx * ny * 2 + 32 * COMPACT_MAX_LINES > budget_bytes:
+        if nx * ny * 2 > budget_bytes:
             continue
         try:
             g = CompactGrid(scenario, c)

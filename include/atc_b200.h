@@ -103,17 +103,21 @@ typedef struct AtcSectorDesc {
     /* wind extension (not in the reference; README.md:64) — NULL / 0 = calm */
     int32_t wind_gx, wind_gy;
     const float *wind;             /* [wind_gy][wind_gx][2] knots (east, north), nodes on the bbox corners */
-    /* optional compact grid, NULL = none: a coarse copy of the accelerator small enough to live in
-       the shared memory of one SM (at most atc_compact_grid_budget() bytes for cells + lines); the rollout kernel
-       with one CTA per SM reads it instead of the fine grid.  Same geometry conventions as the fine grid.
-       cell: bit 15 clear = polygon + 1 for the whole cell (0 = outside); bit 15 set = bits 0-6 line id (127: undecidable
-       here), bits 7-10 / 11-14 answer (polygon + 1) on the positive / negative side of that line.  Points within 1e-9
-       nm of the line and undecidable cells are resolved through the fine grid. */
+    /* optional compact grid, NULL = none: a coarse, two-level copy of the accelerator small enough
+       to live in the shared memory of one SM (at most atc_compact_grid_budget() bytes for cells + lines); the rollout
+       kernel with one CTA per SM reads it instead of the fine grid.  Origin / padding conventions as the fine grid;
+       the kernel takes the float32 index at 1/8 of the cell size (the sub-block resolution) and shifts it down by 3.
+       coarse cell: bit 15 clear = polygon + 1 for the whole cell (0 = outside); bit 15 set, line id (bits 0-6) < 126 =
+       one boundary line crosses the cell, bits 7-10 / 11-14 = answer (polygon + 1) on its positive / negative side;
+       line id 126 / 127 = refined by the 8 x 8 sub-block number (id & 1) * 256 + bits 7-14 (a block number >=
+       cgrid_n_blocks: undecidable).  Sub-block cells: same encoding, line id 127 = undecidable.  Points within 1e-9 nm
+       of their line and undecidable cells are resolved through the fine grid. */
     int32_t cgrid_nx, cgrid_ny;
-    double cgrid_inv_cell;
+    double cgrid_inv_cell;         /* 1 / size of the SUB-block cells (= 8 / coarse cell size) */
     double cgrid_x0, cgrid_y0;
-    const uint16_t *cgrid_cell;    /* [cgrid_ny][cgrid_nx] */
-    int32_t n_cline;               /* <= 127 */
+    const uint16_t *cgrid_cell;    /* [cgrid_ny * cgrid_nx] coarse cells, then [cgrid_n_blocks][8][8] sub-blocks */
+    int32_t cgrid_n_blocks;        /* <= 511 */
+    int32_t n_cline;               /* <= 126 */
     const double *cline;           /* [n_cline][4]: a, b, c (a*a + b*b = 1), 0 */
 } AtcSectorDesc;
 

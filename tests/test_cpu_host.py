@@ -314,7 +314,7 @@ def test_compact_grid_is_exact(scn):
     budget = int(nat.lib().atc_compact_grid_budget())
     assert 100 * 1024 < budget < 227 * 1024
     cg = build_compact_grid(s, budget)
-    assert cg is not None and cg.nbytes <= budget and cg.n_lines <= 127
+    assert cg is not None and cg.nbytes <= budget and cg.n_lines <= 126 and cg.n_blocks <= 511
     assert build_compact_grid(s, 1024) is None                      # nothing fits
     rng = np.random.RandomState(4)
     b = fine.bbox
@@ -326,26 +326,26 @@ def test_compact_grid_is_exact(scn):
             ex = ring[i - 1][0] + t * (ring[i][0] - ring[i - 1][0]); ey = ring[i - 1][1] + t * (ring[i][1] - ring[i - 1][1])
             for d in (0.0, 1e-12, -1e-12, 1e-9, -1e-9, 3e-9, -3e-9, 1e-6, -1e-6, 1e-3):
                 xs.append(ex + d); ys.append(ey - d)
-    k = rng.randint(0, cg.grid_nx, 20000); l = rng.randint(0, cg.grid_ny, 20000)      # cell borders and corners
+    k = rng.randint(0, 8 * cg.grid_nx, 40000); l = rng.randint(0, 8 * cg.grid_ny, 40000)   # (sub-)cell borders, corners
     for d in (0.0, 1e-9, -1e-9, 1e-6, -1e-6):
-        xs.append(cg.grid_x0 + k * cg.cell + d); ys.append(cg.grid_y0 + l * cg.cell + rng.uniform(0, cg.cell, 20000))
-        xs.append(cg.grid_x0 + k * cg.cell + d); ys.append(cg.grid_y0 + l * cg.cell - d)
+        xs.append(cg.grid_x0 + k * cg.cell / 8 + d); ys.append(cg.grid_y0 + l * cg.cell / 8 + rng.uniform(0, cg.cell, 40000))
+        xs.append(cg.grid_x0 + k * cg.cell / 8 + d); ys.append(cg.grid_y0 + l * cg.cell / 8 - d)
     x, y = np.concatenate(xs), np.concatenate(ys)
     ref = fine.find_mva_np(x, y)
     got, slow = cg.lookup_np(x, y, fine)
     np.testing.assert_array_equal(got, ref)
-    assert slow.mean() < 0.25                                        # most points never touch the fine grid
-    ix, iy = cg.cell_index_np(x, y)
-    for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):               # a neighbouring cell within the margin: same answer
-        fx = (x - cg.grid_x0) * cg.grid_inv_cell; fy = (y - cg.grid_y0) * cg.grid_inv_cell
-        near = (np.abs(fx - np.round(fx)) * cg.cell < cg.margin) if dx else (np.abs(fy - np.round(fy)) * cg.cell < cg.margin)
-        jx = np.clip(ix + dx, 0, cg.grid_nx - 1); jy = np.clip(iy + dy, 0, cg.grid_ny - 1)
-        tx = np.clip(np.floor(fx + (0.5 if dx > 0 else -0.5) * (dx != 0)), 0, cg.grid_nx - 1).astype(np.int64)
-        sel = near & (np.abs(jx - np.floor(fx)) <= 1) & (np.abs(jy - np.floor(fy)) <= 1) & \
-            ((jx == np.floor(fx)) | (np.abs(fx - np.round(fx)) * cg.cell < cg.margin)) & \
-            ((jy == np.floor(fy)) | (np.abs(fy - np.round(fy)) * cg.cell < cg.margin))
-        sel &= (np.abs((jx + 0.5) - fx) <= 0.5 + cg.margin * cg.grid_inv_cell) & \
-               (np.abs((jy + 0.5) - fy) <= 0.5 + cg.margin * cg.grid_inv_cell)
+    assert slow[:n].mean() < 0.01                                    # random points hardly ever need the fine grid
+    # the float32 index may pick the neighbour of the true sub-cell when the point is within the float32 error of a
+    # border: every (sub-)cell's entry holds on the cell grown by `margin`, so forcing the neighbour changes nothing
+    sc = cg.cell / 8
+    ix8, iy8 = cg.cell_index_np(x, y)
+    fx, fy = (x - cg.grid_x0) / sc, (y - cg.grid_y0) / sc
+    for dx, dy in ((1, 0), (-1, 0), (0, 1), (0, -1)):
+        border = (np.floor(fx) + (dx > 0)) if dx else (np.floor(fy) + (dy > 0))
+        dist = np.abs((fx if dx else fy) - border) * sc
+        jx, jy = ix8 + dx, iy8 + dy
+        sel = (dist < cg.margin) & (jx >= 0) & (jy >= 0) & (jx < 8 * cg.grid_nx) & (jy < 8 * cg.grid_ny) & \
+            (ix8 == np.floor(fx)) & (iy8 == np.floor(fy))
         if sel.any():
             g2, _ = cg.lookup_np(x[sel], y[sel], fine, cells=(jx[sel], jy[sel]))
             np.testing.assert_array_equal(g2, ref[sel])
