@@ -354,7 +354,7 @@ def run_gpu(args):
     bytes_per_launch = bytes_rollout(A, t_launch, RAW) * N * t_launch
     achieved = bytes_per_launch / avg_launch_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': 'atc_rollout_pipe_kernel<4,false,false,false> (rollout, T=%d)' % TR,
+                'traffic': None, 'peak_source': peak_src, 'kernel': 'atc_rollout_pipe_kernel<4,false,false,false,14> (one CTA per SM, MVA grid in shared memory; rollout, T=%d)' % TR,
                 'algorithmic_bytes_per_env_step': bytes_rollout(A, t_launch, RAW), 'avg_launch_ms': avg_launch_s * 1e3}
     tp = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(tp):
