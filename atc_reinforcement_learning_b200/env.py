@@ -25,6 +25,9 @@ TERM_NAMES = ('running', 'below_mva', 'left_airspace', 'captured', 'timeout', 's
 _SECTOR_CACHE = {}
 
 
+_COMPACT_CACHE = {}
+
+
 def compile_sector_cached(scenario, cell, wind=None):
     """CompiledSector is a pure function of the scenario data; building the fine MVA grid takes a couple of seconds,
     so identical (scenario, cell) pairs share one compiled sector (wind grids are not cached)."""
@@ -82,9 +85,14 @@ class BatchedAtcEnv(object):
         self._scenario = scenario
         self.sector = compile_sector_cached(scenario, grid_cell, wind)
         if compact_grid and not hasattr(self.sector, 'compact'):
-            # coarse copy of the MVA grid for the shared memory of one SM (sector.CompactGrid); None if it cannot be built
+            # coarse copy of the MVA grid for the shared memory of one SM (sector.CompactGrid); None if it cannot be built.
+            # A pure function of the polygons and the budget: shared between envs (building it takes seconds).
             from .sector import build_compact_grid
-            self.sector.compact = build_compact_grid(scenario, int(nat.lib().atc_compact_grid_budget()))
+            budget = int(nat.lib().atc_compact_grid_budget())
+            key = (budget, tuple((m.height, tuple(m.area_as_list)) for m in scenario.mvas))
+            if key not in _COMPACT_CACHE:
+                _COMPACT_CACHE[key] = build_compact_grid(scenario, budget)
+            self.sector.compact = _COMPACT_CACHE[key]
         elif not compact_grid:
             self.sector = copy.copy(self.sector)
             self.sector.compact = None
