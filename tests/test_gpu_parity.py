@@ -468,3 +468,33 @@ def test_error_behaviour():
     # 2 aircraft x 2 invalid channels x -1.0 on top of the time penalty; shaping is bounded by 2.4 per aircraft
     assert (o_rew < -4.1 + 4.8).all() and (o_rew > -4.1 - 1e-9).all()
     assert not done.any() and not o_done.any()
+
+
+def test_one_cta_per_sm_layout_against_the_oracle_and_the_small_layout(monkeypatch):
+    """The rollout kernel has two layouts: 14 CTAs of one mover + observer pair per SM with the fine MVA
+    grid in global memory, and — for long launches of big batches — one CTA of up to 14 pairs per SM with the compact grid
+    (sector.CompactGrid) in shared memory.  Force the second one for short / small / ragged / windy cases and check it
+    against the oracle; then both layouts against each other, bit for bit, at the bench size."""
+    from atc_reinforcement_learning_b200 import SimParameters
+    monkeypatch.setenv('ATC_B200_BIG_MIN_PAIRS', '1')
+    monkeypatch.setenv('ATC_B200_BIG_MIN_STEPS', '1')
+    run_pair(4096, 4, 200, seed=51, chunk=100)
+    for N, A in ((1, 2), (7, 3), (33, 5), (129, 6), (1000, 8), (2048, 1)):
+        run_pair(N, A, 100, seed=60 + A)
+    rng = np.random.RandomState(99)
+    run_pair(2048, 8, 64, seed=4, wind=rng.uniform(-30, 30, (16, 16, 2)).astype(np.float32))
+    run_pair(1024, 4, 120, seed=41, exact_math=True)
+    run_pair(2048, 2, 300, seed=21, h_bias=True, chunk=150, sector='LOWW')
+    run_pair(64, 1, 60, seed=5, sector='SimpleScenario', random_entrypoints=False)
+    N, A, T = 16384, 4, 96
+    g = torch.Generator(device='cuda').manual_seed(7)
+    acts = (torch.rand(T, N, A, 3, device='cuda', generator=g) * 2 - 1)
+    big = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=5)
+    monkeypatch.setenv('ATC_B200_NO_SMEM_GRID', '1')
+    small = make_env(N, A, SimParameters(1), scenario('LOWW', True), seed=5)
+    ob, os_ = big.rollout(acts), small.rollout(acts)
+    assert torch.equal(ob[0], os_[0]) and torch.equal(ob[1], os_[1]) and torch.equal(ob[2], os_[2])
+    assert torch.equal(ob[3]['term_code'], os_[3]['term_code'])
+    assert torch.equal(ob[3]['original_state'], os_[3]['original_state'])
+    assert torch.equal(big.state, small.state) and torch.equal(big.ep_return, small.ep_return)
+    assert int(ob[2].sum()) > 500                         # episodes ended (and re-spawned) inside the window
