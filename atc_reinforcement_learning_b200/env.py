@@ -9,6 +9,7 @@ include/atc_b200.h.  PyTorch owns every device tensor; the kernels live in csrc/
 
 `AtcGym` is the call-compatible single-env adaptor (N = 1, one aircraft, numpy in / numpy out, no auto-reset).
 """
+import contextlib
 import copy
 import ctypes as C
 
@@ -26,6 +27,7 @@ _SECTOR_CACHE = {}
 
 
 _COMPACT_CACHE = {}
+_NULL_CTX = contextlib.nullcontext()
 
 
 def compile_sector_cached(scenario, cell, wind=None):
@@ -80,6 +82,9 @@ class BatchedAtcEnv(object):
             raise ValueError("BatchedAtcEnv runs on a CUDA device only (there is no CPU path)")
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device available (there is no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self._dev_index = self.device.index
         self.num_envs, self.num_aircraft = int(num_envs), int(num_aircraft)
         self._sim_parameters = sim_parameters
         self._scenario = scenario
@@ -156,6 +161,13 @@ class BatchedAtcEnv(object):
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _on_device(self):
+        """Context that makes the env's GPU current; free when it already is (the common case: the context manager
+        alone costs several microseconds of the ~20 us a single-step call takes on the host)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return _NULL_CTX
+        return torch.cuda.device(self.device)
+
     def close(self):
         if getattr(self, '_handle', None):
             nat.lib().atc_destroy(self._handle)
@@ -190,9 +202,14 @@ class BatchedAtcEnv(object):
         a = actions
         if a.dtype != torch.float32:
             a = a.to(torch.float32)
-        if a.numel() != int(np.prod(shape)):
+        n = self.num_envs * self.num_aircraft * 3
+        for d in lead:
+            n *= d
+        if a.numel() != n:
             raise ValueError("actions must have shape %s, got %s" % (shape, tuple(actions.shape)))
-        return a.reshape(shape).contiguous(), None
+        if a.shape != shape or not a.is_contiguous():
+            a = a.reshape(shape).contiguous()
+        return a, None
 
     def _alloc_io(self, lead, out=None):
         N, A, dev = self.num_envs, self.num_aircraft, self.device
@@ -248,7 +265,7 @@ class BatchedAtcEnv(object):
         discrete space).  A cuda tensor runs device-to-device; a numpy array takes the end-to-end host path
         (pinned H2D, kernel, D2H) and returns numpy arrays."""
         dev_a, host_a = self._as_actions(actions, ())
-        with torch.cuda.device(self.device):
+        with self._on_device():
             if host_a is not None:
                 return self._run_host(host_a, 1, self.autoreset, ())
             io = self._alloc_io((), out)
@@ -266,7 +283,7 @@ class BatchedAtcEnv(object):
         if T < 1:
             raise ValueError("rollout needs at least one step")
         dev_a, host_a = self._as_actions(actions, (T,))
-        with torch.cuda.device(self.device):
+        with self._on_device():
             if host_a is not None:
                 return self._run_host(host_a, T, True, (T,))
             io = self._alloc_io((T,), out)
