@@ -13,13 +13,13 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libatc_b200.so')
 INCLUDE = os.path.join(ROOT, 'include')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_AIRCRAFT = 8
 OBS_DIM = 10
 
 EXPORTS = ['atc_abi_version', 'atc_compact_grid_budget', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
            'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
-           'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render']
+           'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render', 'atc_last_launch_info']
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -64,6 +64,16 @@ class AtcBuffers(C.Structure):
 
 class AtcStepIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('actions', 'obs', 'raw_obs', 'reward', 'done', 'term')]
+
+
+class AtcLaunchInfo(C.Structure):
+    _fields_ = [('kernel', C.c_int32), ('n_steps', C.c_int32), ('grid', C.c_int32), ('block', C.c_int32),
+                ('pairs_per_cta', C.c_int32), ('lanes_per_env', C.c_int32), ('wind', C.c_int32),
+                ('track_actions', C.c_int32), ('exact_math', C.c_int32), ('raw_obs', C.c_int32),
+                ('dyn_smem_bytes', C.c_int64)]
+
+
+KERNEL_NAMES = {0: 'none', 1: 'atc_step_kernel', 2: 'atc_rollout_pipe_kernel', 3: 'atc_rollout_pipe_kernel'}
 
 
 def nvcc_command(out=LIB_PATH):
@@ -125,6 +135,8 @@ def lib():
     L.atc_compact_grid_budget.restype = C.c_int64
     L.atc_launch_count.argtypes = [vp]
     L.atc_launch_count.restype = C.c_int64
+    L.atc_last_launch_info.argtypes = [vp, C.POINTER(AtcLaunchInfo)]
+    L.atc_last_launch_info.restype = C.c_int
     L.atc_last_error.argtypes = [vp]
     L.atc_last_error.restype = C.c_char_p
     for name in ('atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',

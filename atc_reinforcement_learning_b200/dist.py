@@ -35,45 +35,163 @@ def init_from_env(backend=None):
 
 
 class ReturnGather(object):
-    """Gathers last_ep_return[N_local] (float32 copy) from every rank.  `gather()` returns the [world * N_local] tensor
-    on every rank (all_gather).  overlap=True (default on CUDA): copy + collective run on a side stream, so the step
-    stream never waits for them (2 x B200: 18.31 G env-steps/s against 18.14 G with the collective enqueued in order
-    on the step stream, overlap=False)."""
+    """Gathers last_ep_return[N_local] (float32 copy) from every rank.  `gather()` returns the [sum of N_local] tensor
+    (global env order) on every rank (all_gather).  Ranks may own different numbers of envs (shard_envs gives the first
+    ranks one more when the global count does not divide): the per-rank counts are exchanged once at construction,
+    every rank sends a block padded to the largest count, and the padding is dropped on receipt.
+
+    overlap=True (default on CUDA): the 4-byte-per-env snapshot of the log is taken in order on the step stream (so it
+    is a consistent cut between two launches), the collective runs on a side stream and the step stream never waits
+    for it.  Two send buffers alternate, so a snapshot is never overwritten while its collective is still in flight
+    (gather() makes the step stream wait for the collective issued two calls earlier, which has long finished)."""
 
     def __init__(self, n_local, device, overlap=None):
         self.device = torch.device(device)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.n_local = int(n_local)
-        self.send = torch.zeros(self.n_local, dtype=torch.float32, device=self.device)
-        self.recv = torch.zeros(self.world * self.n_local, dtype=torch.float32, device=self.device)
+        cuda = self.device.type == 'cuda'
+        if self.world > 1:
+            mine = torch.tensor([self.n_local], dtype=torch.int64, device=self.device)
+            counts = [torch.zeros_like(mine) for _ in range(self.world)]
+            dist.all_gather(counts, mine)
+            self.counts = [int(c.item()) for c in counts]
+        else:
+            self.counts = [self.n_local]
+        self.n_max = max(self.counts)
+        self.equal = all(c == self.n_max for c in self.counts)
+        self.send = [torch.zeros(self.n_max, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self.padded = torch.zeros(self.world * self.n_max, dtype=torch.float32, device=self.device)
+        self.recv = self.padded if self.equal else torch.zeros(sum(self.counts), dtype=torch.float32, device=self.device)
         if overlap is None:
             overlap = True
-        self.stream = torch.cuda.Stream(self.device) if (self.device.type == 'cuda' and overlap) else None
+        self.stream = torch.cuda.Stream(self.device) if (cuda and overlap) else None
+        self.done = [torch.cuda.Event(), torch.cuda.Event()] if self.stream is not None else None
         self.calls = 0
 
-    def _collect(self, last_ep_return):
-        self.send.copy_(last_ep_return)
+    def _collect(self, send):
         if self.world > 1:
             if self.device.type == 'cuda':
-                dist.all_gather_into_tensor(self.recv, self.send)
+                dist.all_gather_into_tensor(self.padded, send)
             else:
-                parts = [torch.empty_like(self.send) for _ in range(self.world)]
-                dist.all_gather(parts, self.send)
-                self.recv.copy_(torch.cat(parts))
+                parts = [torch.empty_like(send) for _ in range(self.world)]
+                dist.all_gather(parts, send)
+                self.padded.copy_(torch.cat(parts))
         else:
-            self.recv.copy_(self.send)
+            self.padded.copy_(send)
+        if not self.equal:
+            off = 0
+            for r, c in enumerate(self.counts):
+                self.recv[off:off + c].copy_(self.padded[r * self.n_max:r * self.n_max + c])
+                off += c
 
     def gather(self, last_ep_return):
+        k = self.calls & 1
         self.calls += 1
+        send = self.send[k]
         if self.stream is not None:
-            self.stream.wait_stream(torch.cuda.current_stream(self.device))
+            cur = torch.cuda.current_stream(self.device)
+            if self.calls > 2:
+                cur.wait_event(self.done[k])                 # the collective that last read send[k]
+            send[:self.n_local].copy_(last_ep_return)        # snapshot, in order on the step stream
+            self.stream.wait_stream(cur)
             with torch.cuda.stream(self.stream):
-                self._collect(last_ep_return)
+                self._collect(send)
+                self.done[k].record(self.stream)
         else:
-            self._collect(last_ep_return)
+            send[:self.n_local].copy_(last_ep_return)
+            self._collect(send)
         return self.recv
 
     def wait(self):
         if self.stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return self.recv
+
+
+def _cpulist(text):
+    cpus = []
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(cuda_index):
+    """(numa_node, [cpu ids]) of the host cores next to a GPU, from sysfs through the GPU's PCI address (falls back
+    to NVML's ideal-affinity mask).  (None, []) when the platform does not say."""
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(cuda_index)
+        bdf = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = '/sys/bus/pci/devices/' + bdf
+        with open(base + '/local_cpulist') as f:
+            cpus = _cpulist(f.read())
+        node = None
+        try:
+            with open(base + '/numa_node') as f:
+                node = int(f.read())
+        except (OSError, ValueError):
+            pass
+        if cpus:
+            return node, cpus
+    except Exception:
+        pass
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        p = torch.cuda.get_device_properties(cuda_index)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(('%08x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id,
+                                                                        p.pci_device_id)).encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        return None, cpus
+    except Exception:
+        return None, []
+
+
+def pin_rank_to_gpu_numa(local_rank, local_world):
+    """Binds the calling process to host cores next to ITS GPU, so that the pinned staging buffers it allocates
+    afterwards are placed on that NUMA node (first touch) and its copy-engine submissions do not cross the socket
+    interconnect.  The ranks whose GPUs share a node split that node's cores evenly (by local rank).  Returns a dict
+    describing the binding (`original` holds the previous affinity for callers that need all cores again), or None if
+    the topology is unknown — in which case nothing is changed."""
+    import torch
+    try:
+        original = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return None
+    n_gpu = torch.cuda.device_count()
+    mine_node, mine = gpu_local_cpus(local_rank)
+    mine = [c for c in mine if c in set(original)]
+    if not mine:
+        return None
+    # which local ranks share these cores
+    sharers = []
+    for r in range(min(local_world, n_gpu)):
+        _, cpus = gpu_local_cpus(r)
+        if set(cpus) & set(mine):
+            sharers.append(r)
+    if local_rank not in sharers:
+        sharers.append(local_rank)
+    sharers.sort()
+    k, n = sharers.index(local_rank), len(sharers)
+    per = max(1, len(mine) // n)
+    chosen = mine[k * per:(k + 1) * per] if k < n - 1 else mine[k * per:]
+    if not chosen:
+        chosen = mine
+    try:
+        os.sched_setaffinity(0, chosen)
+    except OSError:
+        return None
+    return {'numa_node': mine_node, 'cpus': '%d-%d (%d cores)' % (chosen[0], chosen[-1], len(chosen)),
+            'ranks_sharing_node': n, 'original': original}
+
+
+def restore_affinity(binding):
+    if binding and binding.get('original'):
+        try:
+            os.sched_setaffinity(0, binding['original'])
+        except OSError:
+            pass

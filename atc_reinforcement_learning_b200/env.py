@@ -190,6 +190,27 @@ class BatchedAtcEnv(object):
     def launch_count(self):
         return int(nat.lib().atc_launch_count(self._handle))
 
+    @property
+    def last_launch(self):
+        """What the last step() / rollout() actually launched (atc_last_launch_info): kernel name with its template
+        arguments, grid, block, pairs per CTA, steps, dynamic shared memory — for truthful benchmark labels."""
+        info = nat.AtcLaunchInfo()
+        nat.check(self._handle, nat.lib().atc_last_launch_info(self._handle, C.byref(info)))
+        d = {k: int(getattr(info, k)) for k, _ in nat.AtcLaunchInfo._fields_}
+        b = lambda v: 'true' if v else 'false'
+        name = nat.KERNEL_NAMES.get(d['kernel'], '?')
+        if d['kernel'] == 1:
+            name += '<%d,%s,%s,%s>' % (d['lanes_per_env'], b(d['wind']), b(d['track_actions']), b(d['exact_math']))
+        elif d['kernel'] in (2, 3):
+            name += '<%d,%s,%s,%s,%d>' % (d['lanes_per_env'], b(d['wind']), b(d['track_actions']), b(d['exact_math']),
+                                          14 if d['kernel'] == 3 else 1)
+        d['name'] = name
+        d['layout'] = {1: 'fused step kernel, 64-thread CTAs',
+                       2: 'one mover + observer warp pair per 64-thread CTA, MVA grid through L1 / L2',
+                       3: 'one CTA per SM, %d mover + observer warp pairs, compact MVA grid in shared memory'
+                          % d['pairs_per_cta']}.get(d['kernel'], 'none')
+        return d
+
     # ------------------------------------------------------------------------------------------ validation helpers
     def _as_actions(self, actions, lead):
         shape = tuple(lead) + (self.num_envs, self.num_aircraft, 3)
@@ -215,6 +236,7 @@ class BatchedAtcEnv(object):
         N, A, dev = self.num_envs, self.num_aircraft, self.device
         lead = tuple(lead)
         if out is not None:
+            self._check_io(out, lead, host=False)
             return out
         io = {'obs': torch.empty(lead + (N, A, 10), dtype=torch.float32, device=dev),
               'reward': torch.empty(lead + (N,), dtype=torch.float32, device=dev),
@@ -223,6 +245,35 @@ class BatchedAtcEnv(object):
         if self.return_raw_obs:
             io['raw_obs'] = torch.empty(lead + (N, A, 10), dtype=torch.float32, device=dev)
         return io
+
+    _IO_SPEC = {'obs': (torch.float32, 'A10'), 'raw_obs': (torch.float32, 'A10'), 'reward': (torch.float32, ''),
+                'done': (torch.uint8, ''), 'term': (torch.int32, '')}
+
+    def _check_io(self, io, lead, host):
+        """The C ABI receives raw pointers: every caller-supplied output tensor must have exactly the element count,
+        dtype, placement and contiguity the kernels / copies assume, or the call would write out of bounds."""
+        N, A = self.num_envs, self.num_aircraft
+        n_lead = 1
+        for d in lead:
+            n_lead *= int(d)
+        for k in ('obs', 'reward', 'done'):
+            if io.get(k) is None:
+                raise ValueError("out[%r] is required" % k)
+        for k, t in io.items():
+            if t is None:
+                continue
+            if k not in self._IO_SPEC:
+                raise ValueError("unknown output %r" % k)
+            dt, kind = self._IO_SPEC[k]
+            want = n_lead * N * (A * 10 if kind else 1)
+            if not torch.is_tensor(t) or t.dtype != dt or not t.is_contiguous() or t.numel() != want:
+                raise ValueError("out[%r] must be a contiguous %s tensor with %d elements (lead %s)"
+                                 % (k, dt, want, tuple(lead)))
+            if host:
+                if t.device.type != 'cpu' or not t.is_pinned():
+                    raise ValueError("out[%r] must be a pinned host tensor" % k)
+            elif t.device != self.device:
+                raise ValueError("out[%r] lives on %s, env on %s" % (k, t.device, self.device))
 
     def _step_io(self, actions, io):
         return nat.AtcStepIO(actions=actions.data_ptr(), obs=io['obs'].data_ptr(),
@@ -305,13 +356,23 @@ class BatchedAtcEnv(object):
         h = {'T': T,
              'h_actions': pin(lead + (N, A, 3), torch.float32),
              'h': {'obs': pin(lead + (N, A, 10), torch.float32), 'reward': pin(lead + (N,), torch.float32),
-                   'done': pin(lead + (N,), torch.uint8), 'term': pin(lead + (N,), torch.int32)},
-             'd_actions': torch.empty(lead + (N, A, 3), dtype=torch.float32, device=self.device),
-             'd': self._alloc_io(lead)}
+                   'done': pin(lead + (N,), torch.uint8), 'term': pin(lead + (N,), torch.int32)}}
+        st = self._device_staging(T)
+        h['d_actions'], h['d'] = st['d_actions'], st['d']
         if self.return_raw_obs:
             h['h']['raw_obs'] = pin(lead + (N, A, 10), torch.float32)
         self._host = h
         return h
+
+    def _device_staging(self, T):
+        """Device-side staging of the host-buffer path (actions in, outputs out), cached per T.  Separate from the
+        pinned host buffers: rollout_pinned() with caller-owned pinned tensors must not touch those."""
+        st = getattr(self, '_staging', None)
+        if st is None or st['T'] != T:
+            N, A = self.num_envs, self.num_aircraft
+            st = self._staging = {'T': T, 'd_actions': torch.empty((T, N, A, 3), dtype=torch.float32, device=self.device),
+                                  'd': self._alloc_io((T,))}
+        return st
 
     def _run_host(self, host_actions, T, autoreset, lead):
         hb = self._host_buffers(T)
@@ -349,7 +410,10 @@ class BatchedAtcEnv(object):
             raise ValueError("h_actions must be a pinned, contiguous float32 host tensor")
         if h_actions.numel() != T * self.num_envs * self.num_aircraft * 3:
             raise ValueError("h_actions must have shape [T, N, A, 3]")
-        hb = self._host_buffers(T)
+        self._check_io(h_out, (T,), host=True)
+        if h_out.get('raw_obs') is not None and not self.return_raw_obs:
+            raise ValueError("h_out['raw_obs'] given but the env was created with return_raw_obs=False")
+        hb = self._device_staging(T)
         hio = self._step_io(h_actions, h_out)
         dio = self._step_io(hb['d_actions'], hb['d'])
         with torch.cuda.device(self.device):

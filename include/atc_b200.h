@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ATC_ABI_VERSION 3
+#define ATC_ABI_VERSION 4
 #define ATC_MAX_AIRCRAFT 8
 #define ATC_MAX_MVA 31
 #define ATC_OBS_DIM 10
@@ -222,6 +222,25 @@ int atc_render(AtcHandle *h, uint8_t *rgb, int width, int height, const double *
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t atc_launch_count(const AtcHandle *h);
+
+/* Which kernel the last atc_step / atc_rollout (or the last chunk of a *_host call) launched, and in which shape —
+ * so that a benchmark labels what actually ran instead of what it expected to run. */
+typedef enum AtcKernelId {
+    ATC_KERNEL_NONE = 0,
+    ATC_KERNEL_STEP_FUSED = 1,        /* atc_step_kernel: one lane does everything (gym step(), short launches) */
+    ATC_KERNEL_ROLLOUT_PIPE = 2,      /* atc_rollout_pipe_kernel<.., PAIRS = 1>: one mover + observer pair per CTA */
+    ATC_KERNEL_ROLLOUT_PIPE_SM = 3    /* atc_rollout_pipe_kernel<.., PAIRS = 14>: one CTA per SM, MVA grid in shared memory */
+} AtcKernelId;
+typedef struct AtcLaunchInfo {
+    int32_t kernel;                /* AtcKernelId */
+    int32_t n_steps;               /* env steps fused into the launch */
+    int32_t grid, block;           /* CTAs, threads per CTA */
+    int32_t pairs_per_cta;         /* mover + observer warp pairs per CTA (0 for the fused kernel) */
+    int32_t lanes_per_env;         /* G = next_pow2(n_aircraft) */
+    int32_t wind, track_actions, exact_math, raw_obs;   /* template / output switches in effect */
+    int64_t dyn_smem_bytes;
+} AtcLaunchInfo;
+int atc_last_launch_info(const AtcHandle *h, AtcLaunchInfo *out);
 const char *atc_last_error(const AtcHandle *h);   /* h may be NULL: last atc_create error */
 
 #ifdef __cplusplus

@@ -643,6 +643,19 @@ void atc_oracle_rollout(Oracle *o, int T, const float *actions, float *obs, doub
                      done + (size_t)o->n_env * t, term + (size_t)o->n_env * t, 1);
 }
 
+/* same, also returning info["original_state"] (atc_gym.py:192): the raw observation of the moved aircraft of every
+ * step, terminal steps of auto-reset envs included.  raw_obs [T, n_env, n_ac, 10]. */
+void atc_oracle_rollout_raw(Oracle *o, int T, const float *actions, float *obs, float *raw_obs, double *reward,
+                            uint8_t *done, int32_t *term)
+{
+    const size_t na = (size_t)o->n_env * o->n_ac;
+#pragma omp parallel for schedule(static)
+    for (int e = 0; e < o->n_env; ++e)
+        for (int t = 0; t < T; ++t)
+            step_env(o, e, actions + 3 * na * t, obs + 10 * na * t, raw_obs ? raw_obs + 10 * na * t : NULL,
+                     reward + (size_t)o->n_env * t, done + (size_t)o->n_env * t, term + (size_t)o->n_env * t, 1);
+}
+
 void atc_oracle_get_state(const Oracle *o, double *state /* [n_env*n_ac*5] x,y,h,phi,v */, int32_t *timesteps)
 {
     size_t na = (size_t)o->n_env * o->n_ac;

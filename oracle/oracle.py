@@ -137,14 +137,21 @@ class Oracle(object):
                               _p(done, C.c_uint8), _p(term, C.c_int32), C.c_int(autoreset))
         return obs, raw, rew, done, term
 
-    def rollout(self, actions):
-        """actions [T, n_env, n_ac, 3] float32, autoreset on."""
+    def rollout(self, actions, raw=False):
+        """actions [T, n_env, n_ac, 3] float32, autoreset on.  Returns (obs, reward, done, term); with raw=True
+        (obs, raw_obs, reward, done, term), raw_obs = info["original_state"] of every step (atc_gym.py:192)."""
         a = np.ascontiguousarray(actions, np.float32)
         T = a.shape[0]
         obs = np.zeros((T, self.n_env, self.n_ac, 10), np.float32)
         rew = np.zeros((T, self.n_env), np.float64)
         done = np.zeros((T, self.n_env), np.uint8)
         term = np.zeros((T, self.n_env), np.int32)
+        if raw:
+            raw_obs = np.zeros((T, self.n_env, self.n_ac, 10), np.float32)
+            lib().atc_oracle_rollout_raw(self._h, C.c_int(T), _p(a, C.c_float), _p(obs, C.c_float),
+                                         _p(raw_obs, C.c_float), _p(rew, C.c_double), _p(done, C.c_uint8),
+                                         _p(term, C.c_int32))
+            return obs, raw_obs, rew, done, term
         lib().atc_oracle_rollout(self._h, C.c_int(T), _p(a, C.c_float), _p(obs, C.c_float), _p(rew, C.c_double),
                                  _p(done, C.c_uint8), _p(term, C.c_int32))
         return obs, rew, done, term

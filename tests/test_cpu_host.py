@@ -284,6 +284,31 @@ def test_oracle_separation_rule():
     assert (rew[(term & 0xFF) == 5] < -190).all() and (rew[(term & 0xFF) == 0] > -1).all()
 
 
+def test_oracle_rollout_raw_equals_stepwise():
+    """rollout(raw=True) is T x step(autoreset=True): same obs / reward / flags, and info["original_state"] is the raw
+    observation of the moved aircraft on every row — on the terminal rows of auto-reset envs too, where `obs` already
+    holds the reset observation (atc_gym.py:192 returns the pre-reset state)."""
+    N, A, T = 64, 2, 400
+    acts = _acts(np.random.RandomState(5), T, N, A)
+    o1 = Oracle('LOWW', True, n_env=N, n_ac=A, seed=9); o1.reset()
+    o2 = Oracle('LOWW', True, n_env=N, n_ac=A, seed=9); o2.reset()
+    obs, raw, rew, done, term = o1.rollout(acts, raw=True)
+    assert done.sum() > 10
+    for t in range(T):
+        s_obs, s_raw, s_rew, s_done, s_term = o2.step(acts[t], autoreset=True)
+        np.testing.assert_array_equal(obs[t], s_obs)
+        np.testing.assert_array_equal(raw[t], s_raw)
+        np.testing.assert_array_equal(rew[t], s_rew)
+        np.testing.assert_array_equal(done[t], s_done)
+    # on a terminal row the two observations differ (reset obs vs the terminal state); elsewhere obs = normalise(raw)
+    t, e = np.argwhere(done)[0]
+    assert not np.allclose(obs[t, e], raw[t, e])
+    c = o1.constants()
+    live = ~done.astype(bool)
+    norm = (raw[live] - c['nmin'].astype(np.float32) - 0.5 * c['nmax'].astype(np.float32)) / (0.5 * c['nmax'].astype(np.float32))
+    np.testing.assert_allclose(obs[live], norm, rtol=1e-6, atol=1e-6)
+
+
 def test_oracle_autoreset_and_metrics():
     N, A, T = 256, 1, 700
     o = Oracle('LOWW', n_env=N, n_ac=A)

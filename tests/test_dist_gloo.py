@@ -41,10 +41,12 @@ def _worker(rank, world, port, n_global, n_ac, T, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_and_return_gather(tmp_path):
+@pytest.mark.parametrize('n_global', [96, 97])
+def test_two_rank_sharding_and_return_gather(tmp_path, n_global):
+    """97 envs on 2 ranks: unequal shards (49 + 48) — the gather pads to the largest shard and drops the padding."""
     from atc_reinforcement_learning_b200.dist import shard_envs
     from oracle.oracle import Oracle
-    n_global, n_ac, T, world = 96, 4, 300, 2
+    n_ac, T, world = 4, 300, 2
     port = _free_port()
     mp.spawn(_worker, args=(world, port, n_global, n_ac, T, str(tmp_path)), nprocs=world, join=True)
     rng = np.random.RandomState(0)

@@ -140,7 +140,7 @@ def run_pair(N, A, T, seed, sector='LOWW', random_entrypoints=True, wind=None, d
     acts = np.repeat(rng.uniform(-amp, amp, ((T + repeat - 1) // repeat, N, A, 3)).astype(np.float32), repeat, 0)[:T]
     if h_bias:
         acts[..., 1] = -np.abs(acts[..., 1]) * 0.3 - 0.7
-    o_obs, o_rew, o_done, o_term = ora.rollout(acts)
+    o_obs, o_raw, o_rew, o_done, o_term = ora.rollout(acts, raw=True)
     chunk = chunk or T
     outs = []
     for s in range(0, T, chunk):
@@ -152,6 +152,9 @@ def run_pair(N, A, T, seed, sector='LOWW', random_entrypoints=True, wind=None, d
     np.testing.assert_array_equal(g_term, o_term)
     np.testing.assert_allclose(g_rew, o_rew, rtol=OBS_RTOL, atol=OBS_ATOL)
     np.testing.assert_allclose(g_obs, o_obs, rtol=OBS_RTOL, atol=OBS_ATOL)
+    # info["original_state"] (atc_gym.py:192): the raw observation of the MOVED aircraft on every row, the terminal
+    # rows of auto-reset envs included (there `obs` holds the reset observation instead)
+    np.testing.assert_allclose(g_raw, o_raw, rtol=OBS_RTOL, atol=OBS_ATOL)
     st, ts = env.get_state()
     ost, ots = ora.get_state()
     np.testing.assert_array_equal(ts.cpu().numpy(), ots)
@@ -166,7 +169,8 @@ def run_pair(N, A, T, seed, sector='LOWW', random_entrypoints=True, wind=None, d
     np.testing.assert_allclose(env.last_ep_return.cpu().numpy(), m['last_ep_return'], rtol=rt, atol=at)
     codes = np.bincount((o_term & 0xFF)[o_done > 0], minlength=6)
     return {'dones': int(o_done.sum()), 'codes': codes.tolist(),
-            'max_obs_err': float(np.abs(g_obs - o_obs).max()), 'max_rew_err': float(np.abs(g_rew - o_rew).max())}
+            'max_obs_err': float(np.abs(g_obs - o_obs).max()), 'max_rew_err': float(np.abs(g_rew - o_rew).max()),
+            'max_raw_err': float(np.abs(g_raw - o_raw).max()), 'last_launch': env.last_launch}
 
 
 def test_config1_single_env():
@@ -184,6 +188,48 @@ def test_config3_16384x4_separation():
     r = run_pair(16384, 4, 160, seed=3, chunk=80)
     print(r)
     assert r['codes'][2] > 1000
+
+
+def test_bench_shape_16384x4_T1024_vs_oracle():
+    """The launch bench.py times — 16384 envs x 4 aircraft, ONE rollout launch of 1024 steps, default layout selection
+    (one CTA per SM, compact MVA grid in shared memory) — against the oracle on every row of every env: obs,
+    info["original_state"], reward bit-for-tolerance, done / term bit-exact, final state, counters.  The oracle
+    replays the batch in blocks of 2048 envs (env_index_base) to bound host memory."""
+    from atc_reinforcement_learning_b200 import SimParameters
+    from oracle.oracle import Oracle
+    N, A, T, seed, blk = 16384, 4, 1024, 11, 2048
+    env = make_env(N, A, SimParameters(1.0), scenario('LOWW', True), seed=seed)
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    acts = (torch.rand((T + 19) // 20, N, A, 3, device='cuda', generator=g) * 2 - 1).repeat_interleave(20, 0)[:T]
+    acts = acts.contiguous()
+    obs, rew, done, info = env.rollout(acts)
+    torch.cuda.synchronize()
+    ll = env.last_launch
+    print(ll)
+    assert ll['kernel'] == 3 and ll['n_steps'] == T and ll['pairs_per_cta'] == 14, ll
+    st, ts = env.get_state()
+    worst = {'obs': 0.0, 'raw': 0.0, 'rew': 0.0}
+    n_done = 0
+    for b0 in range(0, N, blk):
+        ora = Oracle('LOWW', True, n_env=blk, n_ac=A, seed=seed, env_index_base=b0)
+        ora.reset()                   # the env constructor resets once (atc_gym.py:61) and nothing else has run
+        a = acts[:, b0:b0 + blk].cpu().numpy()
+        o_obs, o_raw, o_rew, o_done, o_term = ora.rollout(a, raw=True)
+        np.testing.assert_array_equal(done[:, b0:b0 + blk].cpu().numpy().astype(np.uint8), o_done)
+        np.testing.assert_array_equal(info['term_code'][:, b0:b0 + blk].cpu().numpy(), o_term)
+        for name, gpu, ref in (('obs', obs, o_obs), ('raw', info['original_state'], o_raw), ('rew', rew, o_rew)):
+            gv = gpu[:, b0:b0 + blk].cpu().numpy()
+            np.testing.assert_allclose(gv, ref, rtol=OBS_RTOL, atol=OBS_ATOL, err_msg=name)
+            worst[name] = max(worst[name], float(np.abs(gv - ref).max()))
+        ost, ots = ora.get_state()
+        np.testing.assert_array_equal(ts[b0:b0 + blk].cpu().numpy(), ots)
+        np.testing.assert_allclose(st[b0:b0 + blk].cpu().numpy(), ost, rtol=0, atol=1e-9)
+        m = ora.metrics()
+        np.testing.assert_array_equal(env.episodes[b0:b0 + blk].cpu().numpy(), m['episodes'])
+        np.testing.assert_array_equal(env.last_ep_len[b0:b0 + blk].cpu().numpy(), m['last_ep_len'])
+        n_done += int(o_done.sum())
+    print(worst, 'episodes finished per env: %.2f' % (n_done / N))
+    assert n_done >= 2 * N          # every env has been through auto-reset about twice or more
 
 
 def test_dense_traffic_separation_vs_oracle():
