@@ -70,7 +70,7 @@ class AtcLaunchInfo(C.Structure):
     _fields_ = [('kernel', C.c_int32), ('n_steps', C.c_int32), ('grid', C.c_int32), ('block', C.c_int32),
                 ('pairs_per_cta', C.c_int32), ('lanes_per_env', C.c_int32), ('wind', C.c_int32),
                 ('track_actions', C.c_int32), ('exact_math', C.c_int32), ('raw_obs', C.c_int32),
-                ('dyn_smem_bytes', C.c_int64)]
+                ('cfg', C.c_int32), ('reserved', C.c_int32), ('dyn_smem_bytes', C.c_int64)]
 
 
 KERNEL_NAMES = {0: 'none', 1: 'atc_step_kernel', 2: 'atc_rollout_pipe_kernel', 3: 'atc_rollout_pipe_kernel'}

@@ -202,7 +202,7 @@ class BatchedAtcEnv(object):
         if d['kernel'] == 1:
             name += '<%d,%s,%s,%s>' % (d['lanes_per_env'], b(d['wind']), b(d['track_actions']), b(d['exact_math']))
         elif d['kernel'] in (2, 3):
-            name += '<%d,%s,%s,%s,%d>' % (d['lanes_per_env'], b(d['wind']), b(d['track_actions']), b(d['exact_math']),
+            name += '<%d,%s,%s,%d,%d>' % (d['lanes_per_env'], b(d['wind']), b(d['track_actions']), d['cfg'],
                                           14 if d['kernel'] == 3 else 1)
         d['name'] = name
         d['layout'] = {1: 'fused step kernel, 64-thread CTAs',

@@ -238,6 +238,9 @@ typedef struct AtcLaunchInfo {
     int32_t pairs_per_cta;         /* mover + observer warp pairs per CTA (0 for the fused kernel) */
     int32_t lanes_per_env;         /* G = next_pow2(n_aircraft) */
     int32_t wind, track_actions, exact_math, raw_obs;   /* template / output switches in effect */
+    int32_t cfg;                   /* rollout kernels: 0 = run-time switches, 1 / 2 = common configuration compiled in
+                                      (normalise + shaping + term + auto-reset; 2 also writes raw_obs) */
+    int32_t reserved;
     int64_t dyn_smem_bytes;
 } AtcLaunchInfo;
 int atc_last_launch_info(const AtcHandle *h, AtcLaunchInfo *out);
