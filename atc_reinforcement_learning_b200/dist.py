@@ -28,9 +28,23 @@ def init_from_env(backend=None):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         if backend is None:
             backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        opts = None
         if backend == 'nccl':
             torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+            # The only collectives of this path are tiny (the 64 KiB episode-return log, a few scalars): one CTA each.
+            # The rollout kernel keeps one CTA resident on (almost) every SM for the whole launch, so a multi-CTA
+            # NCCL kernel cannot run beside it — it would wait for the launch to end and then delay the next one
+            # (measured on 2 x B200: ~70 us per launch, 4.4 % of the step rate); a single CTA fits on a spare SM.
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = 1
+                opts.config.min_ctas = 1
+            except Exception:
+                opts = None
+        if opts is not None:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world, pg_options=opts)
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
     return rank, world, local_rank
 
 

@@ -306,6 +306,52 @@ def parity_in_run(args, env_factory, acts, out, rank, timed_launch):
     return res
 
 
+def quick_config(args, name, dev, peak, launches=10):
+    """Short leg of another BASELINE config: `launches` back-to-back rollout launches of --rollout env-steps timed on
+    the device after 3 warm-up launches, the roofline of what actually launched, and the parity check of that launch
+    shape against the oracle."""
+    import copy
+    import torch
+    from atc_reinforcement_learning_b200 import BatchedAtcEnv, LOWW, SimParameters
+    a2 = copy.copy(args)
+    a2.config = name
+    c = CONFIGS[name]
+    N, A, TR, RAW = c['n_envs'], c['n_aircraft'], args.rollout, bool(args.raw_obs)
+    wind = wind_grid() if c['wind'] else None
+
+    def make():
+        return BatchedAtcEnv(N, A, SimParameters(1), LOWW(random_entrypoints=True), device=dev, seed=0,
+                             return_raw_obs=RAW, grid_cell=args.grid_cell, wind=wind)
+    env = make()
+    g = torch.Generator(device=dev).manual_seed(1234)
+    acts = (torch.rand((TR + ACTION_REPEAT - 1) // ACTION_REPEAT, N, A, 3, device=dev, generator=g) * 2 - 1)
+    acts = acts.repeat_interleave(ACTION_REPEAT, 0)[:TR].contiguous()
+    out = env._alloc_io((TR,))
+    for _ in range(3):
+        env.rollout(acts, out=out)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(launches):
+        env.rollout(acts, out=out)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / launches
+    ll = env.last_launch
+    bpe = bytes_rollout(A, ll['n_steps'], RAW)
+    achieved = bpe * N * ll['n_steps'] / (ms * 1e-3) / 1e9
+    res = {'workload': workload_config(a2)['workload'], 'value': N * TR / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+           'steps': launches, 'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                                           'frac': achieved / peak, 'kernel': '%s (%s)' % (ll['name'], ll['layout']),
+                                           'algorithmic_bytes_per_env_step': bpe}}
+    if not args.skip_parity:
+        res['parity_in_run'] = parity_in_run(a2, make, acts, out, 0, ll)
+    env.close()
+    del env, acts, out
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -490,6 +536,15 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
+    # ---- the other BASELINE configs, short legs (1-GPU runs only): device-timed value, roofline, parity in run
+    others = None
+    if world == 1 and not args.skip_extras and not args.skip_other_configs:
+        del out, acts, env
+        torch.cuda.empty_cache()
+        others = {}
+        for name in sorted(CONFIGS):
+            if name != args.config:
+                others[name] = quick_config(args, name, dev, peak)
     # dominant kernel: the rollout launch (one per bench step); the region also holds, per step, the 64 KB snapshot copy
     # of the return log (a torch kernel, < 3 us) — included in the time, not in the bytes
     avg_launch_s = ms_block * 1e-3 / K
@@ -541,7 +596,7 @@ def run_gpu(args):
             'cuda_graph_ms_per_step': graph_ms,
             'cuda_graph_value': None if graph_ms is None else N / (graph_ms * 1e-3),
             'cuda_graph_roofline_frac': None if graph_ms is None else peak_step / (graph_ms * 1e-3)},
-        'nccl_gathers': gather.calls, 'ms_per_rank': ms_ranks,
+        'other_configs': others, 'nccl_gathers': gather.calls, 'ms_per_rank': ms_ranks,
         'clocks_per_rank': clocks_ranks if world > 1 else None,
     }
     emit(line)
@@ -592,6 +647,8 @@ def main():
     ap.add_argument('--no-pin', action='store_true', help='do not bind the rank to the cores of its GPU\'s NUMA node')
     ap.add_argument('--skip-extras', action='store_true', help='only the device-resident timing (used under ncu)')
     ap.add_argument('--skip-parity', action='store_true')
+    ap.add_argument('--skip-other-configs', action='store_true',
+                    help='do not append the short legs of the other BASELINE configs (4096x1, 16384x8_wind)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

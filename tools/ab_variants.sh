@@ -10,7 +10,8 @@ for rep in $(seq 1 $REPS); do
 for v in variants/*.so; do
   cp $v $LIB
   EXTRA="--skip-parity"; [ $rep = 1 ] && EXTRA=""
-  python bench.py --steps 20 --warmup 5 --skip-extras $EXTRA "$@" 2>/tmp/ab.err | tail -1 | python -c "
+  ENVF=${v%.so}.env; ENVS=""; [ -f $ENVF ] && ENVS=$(cat $ENVF)      # optional environment of the variant (one line)
+  env $ENVS python bench.py --steps 20 --warmup 5 --skip-extras $EXTRA "$@" 2>/tmp/ab.err | tail -1 | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); p=d.get('parity_in_run') or {}
