@@ -454,11 +454,65 @@ class BatchedAtcEnv(object):
     def total_reward(self):
         return self.ep_return
 
-    def get_attr(self, name):
-        """stable-baselines VecEnv-style accessor used by the reference's training callback
-        (learning/atc-gym-stable-baselines.py:34-36)."""
+    # ---- the stable-baselines VecEnv surface the reference's training scripts drive through SubprocVecEnv /
+    # DummyVecEnv (learning/atc-gym-stable-baselines.py:76-85, learning/tune_hyperparameters.py:89-97).  SB 2.8.0 is not
+    # under /root/reference: names and argument meaning are from its published VecEnv base class (unpinned).
+    def _indices(self, indices):
+        if indices is None:
+            return list(range(self.num_envs))
+        if isinstance(indices, int):
+            indices = [indices]
+        idx = [int(i) for i in indices]
+        for i in idx:
+            if not -self.num_envs <= i < self.num_envs:
+                raise IndexError("env index %d out of range" % i)
+        return idx
+
+    def get_attr(self, name, indices=None):
+        """VecEnv.get_attr — used by the reference's training callback (learning/atc-gym-stable-baselines.py:34-36).
+        Per-env device counters come back as a list with one entry per (selected) env."""
         v = getattr(self, name)
-        return v.tolist() if torch.is_tensor(v) else [v] * self.num_envs
+        idx = self._indices(indices)
+        if torch.is_tensor(v) and v.ndim >= 1 and v.shape[0] == self.num_envs:
+            v = v.tolist()
+            return v if indices is None else [v[i] for i in idx]
+        return [v] * len(idx)
+
+    def set_attr(self, name, value, indices=None):
+        """VecEnv.set_attr.  The batch shares one configuration: an attribute can only be set for all envs at once;
+        per-env device counters (timesteps, ep_return, ...) accept a scalar or a sequence for the selected envs."""
+        cur = getattr(self, name, None)
+        if torch.is_tensor(cur) and cur.ndim >= 1 and cur.shape[0] == self.num_envs:
+            idx = torch.as_tensor(self._indices(indices), device=self.device, dtype=torch.long)
+            cur[idx] = torch.as_tensor(value, device=self.device).to(cur.dtype)
+            return
+        if indices is not None and len(self._indices(indices)) != self.num_envs:
+            raise ValueError("%r is shared by the whole batch: set it for all envs (indices=None)" % name)
+        setattr(self, name, value)
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        """VecEnv.env_method: the batched env IS every sub-env, so the method runs once on the batch and its result is
+        repeated per selected env (tensors with a leading env dimension are split per env)."""
+        res = getattr(self, method_name)(*method_args, **method_kwargs)
+        idx = self._indices(indices)
+        if torch.is_tensor(res) and res.ndim >= 1 and res.shape[0] == self.num_envs:
+            return [res[i] for i in idx]
+        return [res] * len(idx)
+
+    def step_async(self, actions):
+        """VecEnv.step_async: enqueue the step on the current CUDA stream and return at once (kernel launches are
+        asynchronous by nature); step_wait() hands out the result tensors."""
+        if getattr(self, '_pending', None) is not None:
+            raise RuntimeError("step_async called twice without step_wait")       # SB's AlreadySteppingError
+        self._pending = self.step(actions)
+
+    def step_wait(self):
+        """VecEnv.step_wait: the (obs, reward, done, info) of the step enqueued by step_async().  The tensors are
+        ordered on the current stream like any other result of step(); nothing blocks the host here."""
+        if getattr(self, '_pending', None) is None:
+            raise RuntimeError("step_wait called without step_async")              # SB's NotSteppingError
+        res, self._pending = self._pending, None
+        return res
 
     def query_mva(self, xy):
         """MVA height [ft] (or -1 outside) for points [n, 2] — the kernel's find_mva (model.py:282-292)."""

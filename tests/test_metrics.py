@@ -123,3 +123,39 @@ def test_env_counters_on_the_device_give_the_oracles_scalars():
     for k in ('simulation/mean_actions', 'simulation/winning_ratio', 'simulation/mean_episode_length'):
         assert got[k] == exp[k], k
     assert got['simulation/mean_episode_return'] == pytest.approx(exp['simulation/mean_episode_return'], rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_vecenv_surface_step_async_env_method_attrs():
+    """The VecEnv calls the reference's scripts make through stable-baselines wrappers
+    (learning/atc-gym-stable-baselines.py:34-36,76-85): step_async / step_wait == step, get_attr / set_attr per env,
+    env_method on the batch.  (SB 2.8.0 itself is not under /root/reference: unpinned.)"""
+    from atc_reinforcement_learning_b200 import BatchedAtcEnv, LOWW, SimParameters
+    N, A = 64, 2
+    mk = lambda: BatchedAtcEnv(N, A, SimParameters(1), LOWW(random_entrypoints=True), seed=3, track_actions=True)
+    e1, e2 = mk(), mk()
+    a = torch.rand(N, A, 3, device='cuda') * 2 - 1
+    for _ in range(5):
+        o1, r1, d1, i1 = e1.step(a)
+        e2.step_async(a)
+        with pytest.raises(RuntimeError):
+            e2.step_async(a)
+        o2, r2, d2, i2 = e2.step_wait()
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.equal(i1['original_state'], i2['original_state'])
+    with pytest.raises(RuntimeError):
+        e2.step_wait()
+    wr = e1.get_attr('winning_ratio')
+    assert len(wr) == N and all(w == 0.0 for w in wr)
+    assert e1.get_attr('timesteps', indices=[0, 5]) == [5, 5]
+    assert e1.get_attr('timestep_limit', indices=3) == [6000]
+    apt = e1.get_attr('actions_per_timestep')
+    assert len(apt) == N and all(0.0 <= v <= 3.0 * A for v in apt)
+    e1.set_attr('timesteps', 17, indices=[2])
+    assert e1.get_attr('timesteps', indices=[1, 2]) == [5, 17]
+    with pytest.raises(ValueError):
+        e1.set_attr('timestep_limit', 10, indices=[0])
+    st = e1.env_method('get_state', indices=[0])
+    assert len(st) == 1 and st[0][0].shape == (N, A, 5)
+    assert e1.env_method('seed', 9) == [[9]] * N
+    e1.close(); e2.close()

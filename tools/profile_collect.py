@@ -27,14 +27,19 @@ KEEP = ['dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum
 def main(tag):
     for src, dst in (('bench.json', '%s_bench.json'), ('bench_reference.json', '%s_bench_reference.json'),
                      ('bench_noraw.json', '%s_bench_noraw.json'), ('bench_T128.json', '%s_bench_T128.json'),
-                     ('launches.csv', '%s_launches.csv'), ('sanitizer_memcheck.log', '%s_sanitizer_memcheck.log'),
+                     ('bench_T20.json', '%s_bench_T20.json'), ('launch_length.json', '%s_launch_length.json'),
+                     ('launches.csv', '%s_launches.csv'), ('launches_4096x1.csv', '%s_launches_4096x1.csv'),
+                     ('launches_16384x8_wind.csv', '%s_launches_16384x8_wind.csv'),
+                     ('sanitizer_memcheck.log', '%s_sanitizer_memcheck.log'),
+                     ('sanitizer_memcheck_big.log', '%s_sanitizer_memcheck_big.log'),
                      ('pytest_gpu.log', '%s_pytest_gpu.log')):
         if os.path.exists(os.path.join(G, src)):
             shutil.copy(os.path.join(G, src), os.path.join(P, dst % tag))
-    rc = os.path.join(G, 'sanitizer_racecheck.log')
-    if os.path.exists(rc):       # keep the summary, not the hundreds of "and Read access" lines
-        keep = [l for l in open(rc) if not l.startswith('=========     and')]
-        open(os.path.join(P, '%s_sanitizer_racecheck.log' % tag), 'w').writelines(keep)
+    for name in ('sanitizer_racecheck', 'sanitizer_racecheck_big'):
+        rc = os.path.join(G, name + '.log')
+        if os.path.exists(rc):       # keep the summary, not the hundreds of "and Read access" lines
+            keep = [l for l in open(rc) if not l.startswith('=========     ')]
+            open(os.path.join(P, '%s_%s.log' % (tag, name)), 'w').writelines(keep)
     rep = os.path.join(G, 'pipe_full.ncu-rep')
     raw, src = os.path.join(G, 'pipe_full_raw.csv'), os.path.join(G, 'pipe_full_src.csv')
     subprocess.run('ncu -i %s --page raw --csv > %s 2>/dev/null' % (rep, raw), shell=True, check=True)
@@ -51,14 +56,22 @@ def main(tag):
         v, u = float(m[name]['value'].replace(',', '')), m[name]['unit']
         return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[u]
     bench = json.loads(open(os.path.join(G, 'bench_under_ncu.json')).read().strip().splitlines()[-1])
-    T = bench['config']['rollout_steps_per_launch']
+    T = bench['roofline']['launch']['n_steps']
     rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')
-    json.dump({'kernel': m['kernel'], 'launch': '16384 envs x 4 aircraft x %d steps, %s' % (T, bench['config']['step_outputs']),
+    cfg = bench['config']
+    # bench.py copies dram_bytes_per_launch into roofline.traffic only when its own timed launch has exactly this shape
+    json.dump({'kernel_name': m['kernel'],
+               'launch': {'n_envs': cfg['envs_per_gpu'], 'n_aircraft': cfg['aircraft_per_env'], 'n_steps': T,
+                          'raw_obs': int(bench['roofline']['launch']['raw_obs']),
+                          'kernel': bench['roofline']['launch']['kernel']},
+               'step_outputs': cfg['step_outputs'],
                'dram_bytes_read': int(rd), 'dram_bytes_written': int(wr), 'dram_bytes_per_launch': int(rd + wr),
-               'rollout_steps_per_launch': T,
+               'algorithmic_bytes_per_launch': bench['roofline']['algorithmic_bytes_per_launch'],
                'source': 'profiles/%s_pipe_kernel_ncu_metrics.json (ncu --set full --clock-control none)' % tag},
               open(os.path.join(P, 'traffic.json'), 'w'), indent=1)
-    n_iter = 2048.0 * T
+    n_iter = 2048.0 * T          # pair-steps of one launch: 65536 aircraft lanes / 32 x T
+    m_inst = float(m['smsp__inst_executed.sum']['value'].replace(',', ''))
+    print('warp instructions per pair-step: %.1f' % (m_inst / n_iter))
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_roles.py'), src, raw, str(n_iter)],
                          capture_output=True, text=True).stdout
     open(os.path.join(P, '%s_pipe_kernel_roles.txt' % tag), 'w').write(out)
