@@ -13,13 +13,14 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libatc_b200.so')
 INCLUDE = os.path.join(ROOT, 'include')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_AIRCRAFT = 8
 OBS_DIM = 10
 
 EXPORTS = ['atc_abi_version', 'atc_compact_grid_budget', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
            'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
-           'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render', 'atc_last_launch_info']
+           'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render', 'atc_last_launch_info', 'atc_vecnorm_run',
+           'atc_vecnorm_last_error', 'atc_vecnorm_scratch_doubles', 'atc_vecnorm_max_steps']
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -66,6 +67,16 @@ class AtcStepIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ('actions', 'obs', 'raw_obs', 'reward', 'done', 'term')]
 
 
+class AtcVecNormState(C.Structure):
+    _fields_ = [('obs_rms', C.c_void_p), ('ret_rms', C.c_void_p), ('ret', C.c_void_p), ('scratch', C.c_void_p),
+                ('scratch_doubles', C.c_int64), ('sync', C.c_void_p), ('nonfinite', C.c_void_p)]
+
+
+class AtcVecNormParams(C.Structure):
+    _fields_ = [('training', C.c_int32), ('norm_obs', C.c_int32), ('norm_reward', C.c_int32), ('reserved', C.c_int32),
+                ('clip_obs', C.c_double), ('clip_reward', C.c_double), ('gamma', C.c_double), ('epsilon', C.c_double)]
+
+
 class AtcLaunchInfo(C.Structure):
     _fields_ = [('kernel', C.c_int32), ('n_steps', C.c_int32), ('grid', C.c_int32), ('block', C.c_int32),
                 ('pairs_per_cta', C.c_int32), ('lanes_per_env', C.c_int32), ('wind', C.c_int32),
@@ -76,15 +87,18 @@ class AtcLaunchInfo(C.Structure):
 KERNEL_NAMES = {0: 'none', 1: 'atc_step_kernel', 2: 'atc_rollout_pipe_kernel', 3: 'atc_rollout_pipe_kernel'}
 
 
+SOURCES = ['atc_kernels.cu', 'atc_vecnorm.cu']
+
+
 def nvcc_command(out=LIB_PATH):
     return ['nvcc', '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-            '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-I', INCLUDE, '-o', out,
-            os.path.join(CSRC, 'atc_kernels.cu')]
+            '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static', '-I', INCLUDE, '-o', out] + \
+           [os.path.join(CSRC, f) for f in SOURCES]
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/atc_kernels.cu for sm_100a into csrc/libatc_b200.so (in-tree, travels to the GPU box)."""
-    src = [os.path.join(CSRC, 'atc_kernels.cu'), os.path.join(INCLUDE, 'atc_b200.h')]
+    """Compile csrc/*.cu for sm_100a into csrc/libatc_b200.so (in-tree, travels to the GPU box)."""
+    src = [os.path.join(CSRC, f) for f in SOURCES] + [os.path.join(INCLUDE, 'atc_b200.h')]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src):
         return LIB_PATH
     if shutil.which('nvcc') is None:
@@ -129,6 +143,15 @@ def lib():
     L.atc_obs_normalize.argtypes = [vp, C.c_int64, C.c_int32, vp, C.c_double, C.c_double, vp, vp]
     L.atc_obs_stats_update.restype = C.c_int
     L.atc_obs_normalize.restype = C.c_int
+    L.atc_vecnorm_run.argtypes = [C.POINTER(AtcVecNormState), C.POINTER(AtcVecNormParams), C.c_int32, C.c_int64, C.c_int32,
+                                  vp, vp, vp, vp, vp, C.c_int, vp]
+    L.atc_vecnorm_run.restype = C.c_int
+    L.atc_vecnorm_scratch_doubles.argtypes = [C.c_int, C.c_int32, C.c_int64, C.c_int32]
+    L.atc_vecnorm_scratch_doubles.restype = C.c_int64
+    L.atc_vecnorm_max_steps.argtypes = [C.c_int]
+    L.atc_vecnorm_max_steps.restype = C.c_int32
+    L.atc_vecnorm_last_error.argtypes = []
+    L.atc_vecnorm_last_error.restype = C.c_char_p
     L.atc_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]
     L.atc_render.restype = C.c_int
     L.atc_compact_grid_budget.argtypes = []

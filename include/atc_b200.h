@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define ATC_ABI_VERSION 4
+#define ATC_ABI_VERSION 5
 #define ATC_MAX_AIRCRAFT 8
 #define ATC_MAX_MVA 31
 #define ATC_OBS_DIM 10
@@ -211,6 +211,38 @@ int atc_obs_stats_update(const float *x, int64_t n_rows, int32_t dim, double *rm
                          void *stream);
 int atc_obs_normalize(const float *x, int64_t n_rows, int32_t dim, const double *rms, double epsilon, double clip,
                       float *out, void *stream);
+
+/* Fused VecNormalize + VecCheckNan (same next-row component; csrc/atc_vecnorm.cu): ONE cooperative launch applies
+ * stable-baselines' VecNormalize.step_wait to n_steps consecutive env steps — per step: ret = ret * gamma + reward;
+ * running moments of the observation rows and of ret updated with the step's batch (training); obs_out =
+ * clip((obs - mean) / sqrt(var + epsilon)), reward_out = clip(reward / sqrt(ret_var + epsilon)); ret[done] = 0 —
+ * as two streaming passes over the rows with one grid-wide barrier in between (the batch totals of the steps are
+ * independent; only their 22-double merge is sequential).
+ * All buffers are caller-owned device memory on `device`; obs_out may alias obs_in, reward_out may alias reward_in.
+ *   obs_in / obs_out     float [n_steps][n_env][n_aircraft][10], 16-byte aligned
+ *   reward_in / _out     float [n_steps][n_env], done uint8 [n_steps][n_env]; reward_in = NULL skips the reward path
+ *                        (the reset() observation: stable-baselines updates and normalises the observation only)
+ * The state persists between calls; initialise obs_rms = {0 x10, 1 x10, 1e-4}, ret_rms = {0, 1, 1e-4}, ret and sync 0.
+ * n_steps <= atc_vecnorm_max_steps(device) per call (longer rollouts: several calls, the state carries over). */
+typedef struct AtcVecNormState {
+    double *obs_rms;       /* [21] running mean[10], var[10], count */
+    double *ret_rms;       /* [3]  running mean, var, count of the discounted return */
+    double *ret;           /* [n_env] discounted return accumulators (may be NULL when reward_in is never given) */
+    double *scratch;       /* [scratch_doubles] work space, contents irrelevant between calls */
+    int64_t scratch_doubles; /* >= atc_vecnorm_scratch_doubles(device, n_steps, n_env, n_aircraft) */
+    uint32_t *sync;        /* [4] grid barrier (count, generation), barrier time-out flag, reserved */
+    int32_t *nonfinite;    /* [1] set to 1 when an observation or reward is NaN / Inf (never cleared by the library) */
+} AtcVecNormState;
+typedef struct AtcVecNormParams {
+    int32_t training, norm_obs, norm_reward, reserved;
+    double clip_obs, clip_reward, gamma, epsilon;
+} AtcVecNormParams;
+int atc_vecnorm_run(const AtcVecNormState *st, const AtcVecNormParams *p, int32_t n_steps, int64_t n_env, int32_t n_aircraft,
+                    const float *obs_in, float *obs_out, const float *reward_in, float *reward_out, const uint8_t *done,
+                    int device, void *stream);
+int64_t atc_vecnorm_scratch_doubles(int device, int32_t n_steps, int64_t n_env, int32_t n_aircraft);   /* -1: bad arguments */
+int32_t atc_vecnorm_max_steps(int device);
+const char *atc_vecnorm_last_error(void);
 
 /* Next-row component: headless replacement of AtcGym.render(mode='rgb_array')
  * (/root/reference/envs/atc/atc_gym.py:367-552, themes.py) — same layout (10 px padding around the sector bbox, scale
