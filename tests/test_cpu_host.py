@@ -374,3 +374,28 @@ def test_compact_grid_is_exact(scn):
         if sel.any():
             g2, _ = cg.lookup_np(x[sel], y[sel], fine, cells=(jx[sel], jy[sel]))
             np.testing.assert_array_equal(g2, ref[sel])
+
+
+def test_row_stores_stay_adjacent_in_sass():
+    """The five 8-byte stores of an observation row must be issued (nearly) back to back in the rollout kernel the bench
+    times: the L1 merges the partial-sector writes of adjacent store instructions only, and a build whose scheduler
+    spreads them between the arithmetic runs 12 % slower at 1.9 x instead of 1.4 x the payload in L1 -> L2 writes
+    (found in round 2 when an unrelated change flipped the schedule).  No GPU needed: cuobjdump."""
+    import importlib.util
+    import shutil
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not available')
+    spec = importlib.util.spec_from_file_location('sass_summary', os.path.join(ROOT, 'tools', 'sass_summary.py'))
+    ss = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ss)
+    from atc_reinforcement_learning_b200 import _native as nat
+    nat.build_library()
+    fns = ss.functions()
+    checked = 0
+    for name, rows in fns.items():
+        if 'atc_rollout_pipe_kernel<4, false, false, 2, 14>' in name or 'atc_rollout_pipe_kernel<4, false, false, 1, 14>' in name:
+            spans = ss.row_store_spans(rows)
+            assert spans, name
+            assert max(spans) <= 10, (name, spans)
+            checked += 1
+    assert checked == 2
