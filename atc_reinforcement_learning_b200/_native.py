@@ -15,12 +15,13 @@ INCLUDE = os.path.join(ROOT, 'include')
 
 ABI_VERSION = 5
 MAX_AIRCRAFT = 8
+TEXT_MAX = 40
 OBS_DIM = 10
 
 EXPORTS = ['atc_abi_version', 'atc_compact_grid_budget', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
            'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
            'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render', 'atc_last_launch_info', 'atc_vecnorm_run',
-           'atc_vecnorm_last_error', 'atc_vecnorm_scratch_doubles', 'atc_vecnorm_max_steps']
+           'atc_vecnorm_last_error', 'atc_vecnorm_scratch_doubles', 'atc_vecnorm_max_steps', 'atc_render_text']
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -87,7 +88,7 @@ class AtcLaunchInfo(C.Structure):
 KERNEL_NAMES = {0: 'none', 1: 'atc_step_kernel', 2: 'atc_rollout_pipe_kernel', 3: 'atc_rollout_pipe_kernel'}
 
 
-SOURCES = ['atc_kernels.cu', 'atc_vecnorm.cu']
+SOURCES = ['atc_kernels.cu', 'atc_vecnorm.cu', 'atc_text.cu']
 
 
 def nvcc_command(out=LIB_PATH):
@@ -154,6 +155,8 @@ def lib():
     L.atc_vecnorm_last_error.restype = C.c_char_p
     L.atc_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]
     L.atc_render.restype = C.c_int
+    L.atc_render_text.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, vp]
+    L.atc_render_text.restype = C.c_int
     L.atc_compact_grid_budget.argtypes = []
     L.atc_compact_grid_budget.restype = C.c_int64
     L.atc_launch_count.argtypes = [vp]

@@ -530,14 +530,15 @@ class BatchedAtcEnv(object):
             nat.check(self._handle, nat.lib().atc_query_corridor(self._handle, q.shape[0], _ptr(q), _ptr(out), self._stream()))
         return out.bool()
 
-    def render(self, mode='rgb_array', env_index=0, trail_xy=None):
+    def render(self, mode='rgb_array', env_index=0, trail_xy=None, labels=True, last_reward=None):
         """AtcGym.render (atc_gym.py:367-552) for one env of the batch, headless: mode 'rgb_array' returns a numpy
-        uint8 image [H, W, 3] drawn by a CUDA kernel (render.py; no text labels).  There is no window system here:
-        mode 'human' raises."""
+        uint8 image [H, W, 3] drawn by CUDA kernels (render.py): sector, runway, approach, aircraft, trail and — with
+        labels=True — the reference's text labels in a 5 x 7 bitmap font.  There is no window system here: mode 'human'
+        raises."""
         if mode != 'rgb_array':
             raise NotImplementedError("only mode='rgb_array' is available (headless; SURVEY.md §2 row 7, §8f rank 4)")
         from .render import render_rgb
-        return render_rgb(self, env_index, trail_xy).cpu().numpy()
+        return render_rgb(self, env_index, trail_xy, labels=labels, last_reward=last_reward).cpu().numpy()
 
 
 class AtcGym(object):
@@ -599,7 +600,8 @@ class AtcGym(object):
         if mode == 'rgb_array':                          # trail: every 5th of the last 25 positions (atc_gym.py:440-447)
             n = len(self._history)
             idx = [i for i in range(n - 5, max(0, n - 25), -1) if i % 5 == 0]
-            return self._env.render(mode, 0, np.asarray([self._history[i] for i in idx], np.float64).reshape(-1, 2))
+            return self._env.render(mode, 0, np.asarray([self._history[i] for i in idx], np.float64).reshape(-1, 2),
+                                    last_reward=self.last_reward)
         return self._env.render(mode)
 
     def close(self):

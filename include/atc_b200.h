@@ -247,10 +247,22 @@ const char *atc_vecnorm_last_error(void);
 /* Next-row component: headless replacement of AtcGym.render(mode='rgb_array')
  * (/root/reference/envs/atc/atc_gym.py:367-552, themes.py) — same layout (10 px padding around the sector bbox, scale
  * from the width; pass height = (int)((bbox_y1 - bbox_y0) * scale) + 20 for the reference's aspect), same elements and
- * colours, no text labels.  rgb: device uint8 [height][width][3], row 0 = north.  trail_xy: device double [n_trail][2]
+ * colours; the text labels are stamped separately by atc_render_text.  rgb: device uint8 [height][width][3], row 0 = north.  trail_xy: device double [n_trail][2]
  * past positions drawn as dots; heads_xy: device double [n_heads][2] current aircraft positions drawn as symbols. */
 int atc_render(AtcHandle *h, uint8_t *rgb, int width, int height, const double *trail_xy, int n_trail,
                const double *heads_xy, int n_heads, void *stream);
+
+/* Text labels over a rendered image (csrc/atc_text.cu) — the reference's pyglet labels (rendering.py:7-23): reward lines
+ * (atc_gym.py:404-412) and the name / "FL  speed" lines next to every aircraft (atc_gym.py:436-443).  Screen coordinates
+ * with the origin bottom-left like the reference's viewer, (x, y) = the label's top-left corner; ColorScheme.label;
+ * 5 x 7 bitmap font (there is no font rasteriser here), lower case drawn as upper case.  labels: DEVICE array. */
+#define ATC_TEXT_MAX 40
+typedef struct AtcTextLabel {
+    float x, y;
+    int32_t bold, n;               /* n characters of text are drawn */
+    char text[ATC_TEXT_MAX];
+} AtcTextLabel;
+int atc_render_text(uint8_t *rgb, int width, int height, const AtcTextLabel *labels, int n_labels, void *stream);
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t atc_launch_count(const AtcHandle *h);

@@ -40,7 +40,7 @@ def test_rendered_image_matches_the_geometry():
     env = BatchedAtcEnv(4, 2, SimParameters(1), LOWW(random_entrypoints=True), seed=3)
     cs = env.sector
     trail = np.array([[30.0, 30.0], [31.0, 31.5]])
-    img = env.render('rgb_array', env_index=2, trail_xy=trail)
+    img = env.render('rgb_array', env_index=2, trail_xy=trail, labels=False)
     W, H = image_size(cs)
     assert img.shape == (H, W, 3) and img.dtype == np.uint8
     scale = 600 / (cs.bbox[2] - cs.bbox[0])
@@ -95,3 +95,51 @@ def test_adaptor_renders_its_own_trail():
     plane = np.all(img == np.array(PLANE, np.uint8), -1)
     assert plane.sum() > 30                                          # symbol outline + 4 trail dots
     env.close()
+
+
+FONT_8 = ['.###.', '#...#', '#...#', '.###.', '#...#', '#...#', '.###.']
+FONT_COLON = ['.....', '.##..', '.##..', '.....', '.##..', '.##..', '.....']
+
+
+@pytest.mark.gpu
+def test_text_labels_are_stamped_at_the_reference_anchor_points():
+    """rendering.py:7-23 / atc_gym.py:404-443: reward lines at (10, 40) and (10, 25), aircraft name and "FL  speed" at
+    rot_matrix(135) . (0, 8) from the symbol, anchored top-left, ColorScheme.label — in a 5 x 7 bitmap font."""
+    from atc_reinforcement_learning_b200 import BatchedAtcEnv, LOWW, SimParameters, make
+    from atc_reinforcement_learning_b200.render import image_size, label_list, stamp_labels
+    # the glyphs themselves: "8:" on a black image, top-left corner at screen (20, 50)
+    H, W = 80, 100
+    img = torch.zeros(H, W, 3, dtype=torch.uint8, device='cuda')
+    stamp_labels(img, [(20.0, 50.0, 0, "8:"), (60.0, 30.0, 1, "1")], img.device)
+    a = (img.cpu().numpy() == np.array(PLANE, np.uint8)).all(-1)
+    top = H - 1 - 49                                                   # image row of screen y = 49, the glyph's top row
+    got8 = [''.join('#' if a[top + r, 20 + c] else '.' for c in range(5)) for r in range(7)]
+    gotc = [''.join('#' if a[top + r, 26 + c] else '.' for c in range(5)) for r in range(7)]
+    assert got8 == FONT_8 and gotc == FONT_COLON
+    one = a[H - 1 - 29:H - 1 - 29 + 7, 60:66]
+    assert one[:, 2:4].all(axis=0).all() and int(one.sum()) > 7 + 7      # bold: the vertical stroke is two pixels wide
+    assert int(a.sum()) == sum(r.count('#') for r in FONT_8 + FONT_COLON) + int(one.sum())
+    # on the env: labels change pixels only inside their boxes, and every label leaves some
+    env = BatchedAtcEnv(3, 2, SimParameters(1), LOWW(random_entrypoints=True), seed=5)
+    plain = env.render('rgb_array', env_index=1, labels=False)
+    lab = env.render('rgb_array', env_index=1, last_reward=-0.05)
+    Wd, Hd = image_size(env.sector)
+    st, _ = env.get_state()
+    ac = st[1].cpu().numpy()
+    items = label_list(env.sector, [(r[0], r[1], r[2], r[4]) for r in ac], float(env.ep_return[1]), -0.05)
+    assert [t for _, _, _, t in items][:2] == ["Total reward: %.2f" % float(env.ep_return[1]), "Last reward: -0.05"]
+    assert items[2][3] == "FLT01" and items[3][3] == "%d  %d" % (round(ac[0][2] / 100), round(ac[0][4] / 10))
+    changed = (plain != lab).any(-1)
+    allowed = np.zeros_like(changed)
+    for x, y, bold, text in items:
+        x0, y1 = int(np.floor(x)), int(np.floor(y))                     # top-left corner, screen coordinates
+        r0, r1 = Hd - 1 - (y1 - 1), Hd - 1 - (y1 - 7)
+        box = (slice(max(r0, 0), max(r1 + 1, 0)), slice(max(x0, 0), x0 + 6 * len(text) + 1))
+        allowed[box] = True
+        assert (lab[box] == np.array(PLANE, np.uint8)).all(-1).any(), text
+    assert changed.any() and not (changed & ~allowed).any()
+    # the single-env adaptor passes its last reward
+    g = make('AtcEnv-v0')
+    g.reset()
+    g.step(np.zeros(3, np.float32))
+    assert g.render('rgb_array').shape == (Hd, Wd, 3)

@@ -7,4 +7,4 @@ cd "$(dirname "$0")/.."
 NAME=$1; shift
 mkdir -p variants
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared -cudart static \
-     -I include -DATC_DEV_FAST "$@" -o variants/$NAME.so atc_reinforcement_learning_b200/csrc/atc_kernels.cu atc_reinforcement_learning_b200/csrc/atc_vecnorm.cu
+     -I include -DATC_DEV_FAST "$@" -o variants/$NAME.so atc_reinforcement_learning_b200/csrc/atc_kernels.cu atc_reinforcement_learning_b200/csrc/atc_vecnorm.cu atc_reinforcement_learning_b200/csrc/atc_text.cu
