@@ -143,3 +143,22 @@ def test_text_labels_are_stamped_at_the_reference_anchor_points():
     g.reset()
     g.step(np.zeros(3, np.float32))
     assert g.render('rgb_array').shape == (Hd, Wd, 3)
+
+
+def test_label_list_follows_the_reference_layout():
+    """atc_gym.py:404-412, 436-443 (no GPU): reward lines at (10, 40) / (10, 25), not bold; per aircraft the name at
+    rot_matrix(135) . (0, 8) from the symbol's screen position and "%d  %d" (flight level, speed / 10) 15 px below, bold."""
+    import math
+    from atc_reinforcement_learning_b200.render import PADDING, label_list
+    cs = _sector()
+    bx0, by0, bx1, by1 = [float(v) for v in cs.bbox]
+    scale = 600 / (bx1 - bx0)
+    items = label_list(cs, [(30.0, 40.0, 15049.0, 246.0), (10.0, 51.0, 3000.0, 200.0, 'AUA12')], 12.3456, -0.05)
+    assert items[0] == (10.0, 40.0, 0, 'Total reward: 12.35') and items[1] == (10.0, 25.0, 0, 'Last reward: -0.05')
+    c, s_ = math.cos(math.radians(135)), math.sin(math.radians(135))          # model.rot_matrix(135) . (0, 8)
+    ex, ey = (30.0 - bx0) * scale + PADDING + 8 * s_, (40.0 - by0) * scale + PADDING + 8 * c
+    x, y, bold, text = items[2]
+    assert (round(x, 9), round(y, 9), bold, text) == (round(ex, 9), round(ey, 9), 1, 'FLT01')
+    assert items[3][:3] == (x, y - 15.0, 1) and items[3][3] == '150  25'       # round(150.49), round(24.6)
+    assert items[4][3] == 'AUA12' and items[5][3] == '30  20'
+    assert label_list(cs, [], None, None) == []
