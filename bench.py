@@ -130,7 +130,12 @@ class ClockSampler(threading.Thread):
             try:
                 mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                self.samples.append((time.perf_counter(), mhz, r))
+                try:
+                    mem = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM))
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    mem, pw = None, None
+                self.samples.append((time.perf_counter(), mhz, r, mem, pw))
             except Exception:
                 pass
             time.sleep(self.period)
@@ -148,12 +153,15 @@ class ClockSampler(threading.Thread):
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         kept = [x for x in self.samples if self.t_begin <= x[0] <= self.t_end] or self.samples[-1:]
         s = sorted(x[1] for x in kept)
-        for _, _, r in kept:
+        for x in kept:
             for bit, name in self.names.items():
-                if r & bit:
+                if x[2] & bit:
                     self.reasons.add(name)
+        mem = sorted(x[3] for x in kept if x[3] is not None)
+        pw = [x[4] for x in kept if x[4] is not None]
         return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
-                'samples': len(s)}
+                'samples': len(s), 'mem_mhz': mem[len(mem) // 2] if mem else None,
+                'power_w_first_last': [round(pw[0]), round(pw[-1])] if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
