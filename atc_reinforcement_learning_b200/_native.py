@@ -21,7 +21,7 @@ OBS_DIM = 10
 EXPORTS = ['atc_abi_version', 'atc_compact_grid_budget', 'atc_create', 'atc_destroy', 'atc_reset', 'atc_step', 'atc_rollout', 'atc_step_host',
            'atc_rollout_host', 'atc_query_mva', 'atc_query_corridor', 'atc_launch_count', 'atc_last_error',
            'atc_obs_stats_update', 'atc_obs_normalize', 'atc_render', 'atc_last_launch_info', 'atc_vecnorm_run',
-           'atc_vecnorm_last_error', 'atc_vecnorm_scratch_doubles', 'atc_vecnorm_max_steps', 'atc_render_text']
+           'atc_vecnorm_last_error', 'atc_vecnorm_scratch_doubles', 'atc_vecnorm_max_steps', 'atc_render_text', 'atc_vecnorm_plan']
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)
@@ -151,6 +151,8 @@ def lib():
     L.atc_vecnorm_scratch_doubles.restype = C.c_int64
     L.atc_vecnorm_max_steps.argtypes = [C.c_int]
     L.atc_vecnorm_max_steps.restype = C.c_int32
+    L.atc_vecnorm_plan.argtypes = [C.c_int, C.c_int, C.c_int32, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
+    L.atc_vecnorm_plan.restype = C.c_int
     L.atc_vecnorm_last_error.argtypes = []
     L.atc_vecnorm_last_error.restype = C.c_char_p
     L.atc_render.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int, vp]

@@ -400,22 +400,10 @@ struct Plan {
     int64_t slab_cols, scratch_doubles;
 };
 
-int make_plan(int device, int32_t n_steps, int64_t n_env, int32_t n_aircraft, Plan *pl)
+// the geometry as a pure function of the machine (SMs, co-resident CTAs per SM) and the job — testable without a GPU
+int plan_for(int n_sm, int per_sm_in, int32_t n_steps, int64_t n_env, int32_t n_aircraft, Plan *pl)
 {
-    // the device queries cost tens of microseconds: remembered per thread for the device last asked about
-    thread_local int c_device = -1, c_sm = 0, c_coop = 0, c_per_sm = 0;
-    if (c_device != device) {
-        int n_sm = 0, coop = 0, p2 = 0, p4 = 0;
-        cudaError_t e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, atc_vecnorm_kernel<2>, kThreads, 0);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, atc_vecnorm_kernel<4>, kThreads, 0);
-        if (e != cudaSuccess) return vn_fail(ATC_ERR_CUDA, cudaGetErrorString(e));
-        c_device = device; c_sm = n_sm; c_coop = coop; c_per_sm = p2 < p4 ? p2 : p4;
-    }
-    const int n_sm = c_sm;
-    if (!c_coop || c_per_sm < 1) return vn_fail(ATC_ERR_UNSUPPORTED, "the device does not support cooperative launches");
-    const int per_sm = c_per_sm > 4 ? 4 : c_per_sm;
+    const int per_sm = per_sm_in > 4 ? 4 : per_sm_in;
     const int64_t cap = (int64_t)n_sm * per_sm;
     const int64_t rows = n_env * n_aircraft;
     const int vec = (rows % 2 == 0) ? 4 : 2;                              // float4 needs every step to start 16-byte aligned
@@ -451,11 +439,39 @@ int make_plan(int device, int32_t n_steps, int64_t n_env, int32_t n_aircraft, Pl
     return ATC_OK;
 }
 
+int make_plan(int device, int32_t n_steps, int64_t n_env, int32_t n_aircraft, Plan *pl)
+{
+    // the device queries cost tens of microseconds: remembered per thread for the device last asked about
+    thread_local int c_device = -1, c_sm = 0, c_coop = 0, c_per_sm = 0;
+    if (c_device != device) {
+        int n_sm = 0, coop = 0, p2 = 0, p4 = 0;
+        cudaError_t e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, atc_vecnorm_kernel<2>, kThreads, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, atc_vecnorm_kernel<4>, kThreads, 0);
+        if (e != cudaSuccess) return vn_fail(ATC_ERR_CUDA, cudaGetErrorString(e));
+        c_device = device; c_sm = n_sm; c_coop = coop; c_per_sm = p2 < p4 ? p2 : p4;
+    }
+    if (!c_coop || c_per_sm < 1) return vn_fail(ATC_ERR_UNSUPPORTED, "the device does not support cooperative launches");
+    return plan_for(c_sm, c_per_sm, n_steps, n_env, n_aircraft, pl);
+}
+
 }  // namespace
 
 extern "C" {
 
 const char *atc_vecnorm_last_error(void) { return g_vn_error; }
+
+int atc_vecnorm_plan(int n_sm, int ctas_per_sm, int32_t n_steps, int64_t n_env, int32_t n_aircraft, int64_t out[6])
+{
+    if (!out || n_sm < 1 || ctas_per_sm < 1 || n_steps < 1 || n_env < 1 || n_aircraft < 1 || n_aircraft > ATC_MAX_AIRCRAFT)
+        return vn_fail(ATC_ERR_INVALID_ARGUMENT, "atc_vecnorm_plan: bad arguments");
+    Plan pl;
+    const int rc = plan_for(n_sm, ctas_per_sm, n_steps, n_env, n_aircraft, &pl);
+    if (rc != ATC_OK) return rc;
+    out[0] = pl.grid; out[1] = pl.slabs; out[2] = pl.slab_cols; out[3] = pl.ret_ctas; out[4] = pl.vec; out[5] = pl.scratch_doubles;
+    return ATC_OK;
+}
 
 int64_t atc_vecnorm_scratch_doubles(int device, int32_t n_steps, int64_t n_env, int32_t n_aircraft)
 {

@@ -242,6 +242,10 @@ int atc_vecnorm_run(const AtcVecNormState *st, const AtcVecNormParams *p, int32_
                     int device, void *stream);
 int64_t atc_vecnorm_scratch_doubles(int device, int32_t n_steps, int64_t n_env, int32_t n_aircraft);   /* -1: bad arguments */
 int32_t atc_vecnorm_max_steps(int device);
+/* The launch geometry atc_vecnorm_run would choose on a machine with n_sm SMs and ctas_per_sm co-resident CTAs per SM (no
+ * GPU needed; tests): out = {CTAs, slabs per step, columns per slab, CTAs running the return recurrence, floats per
+ * load (2 / 4), scratch doubles}. */
+int atc_vecnorm_plan(int n_sm, int ctas_per_sm, int32_t n_steps, int64_t n_env, int32_t n_aircraft, int64_t out[6]);
 const char *atc_vecnorm_last_error(void);
 
 /* Next-row component: headless replacement of AtcGym.render(mode='rgb_array')

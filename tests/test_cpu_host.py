@@ -399,3 +399,41 @@ def test_row_stores_stay_adjacent_in_sass():
             assert max(spans) <= 10, (name, spans)
             checked += 1
     assert checked == 2
+
+
+def test_vecnorm_launch_plan_invariants():
+    """The fused VecNormalize launch (csrc/atc_vecnorm.cu) cuts the T x rows observation rows into (step, slab) tiles;
+    its geometry is a pure function of the machine and the job (atc_vecnorm_plan, no GPU): every column is covered, the
+    slabs start at multiples of 5 columns (a thread keeps its features), no CTA owns more tiles than it has slots for,
+    16-byte loads only when every step starts 16-byte aligned, scratch = what the kernel indexes."""
+    from atc_reinforcement_learning_b200 import _native as nat
+    L = nat.lib()
+    out = (C.c_int64 * 6)()
+    rng = np.random.RandomState(0)
+    cases = [(148, 4, 1, 16384, 4), (148, 4, 1024, 16384, 4), (148, 4, 40, 1, 1), (148, 4, 130, 300, 3), (148, 1, 4736, 7, 1),
+             (132, 2, 2048, 131072, 8), (8, 1, 256, 3, 5)]
+    for _ in range(400):
+        cases.append((int(rng.randint(1, 200)), int(rng.randint(1, 9)), int(rng.randint(1, 600)),
+                      int(2 ** rng.uniform(0, 18)), int(rng.randint(1, 9))))
+    n_ok = 0
+    for n_sm, per_sm, T, N, A in cases:
+        rc = L.atc_vecnorm_plan(n_sm, per_sm, T, N, A, out)
+        if T > 32 * n_sm * min(per_sm, 4):
+            assert rc != 0
+            continue
+        assert rc == 0, (n_sm, per_sm, T, N, A, L.atc_vecnorm_last_error())
+        grid, slabs, slab_cols, ret_ctas, vec, scratch = [int(v) for v in out]
+        rows = N * A
+        n_cols = rows * 10 // vec
+        assert vec == (4 if rows % 2 == 0 else 2) and rows * 10 % vec == 0
+        assert 1 <= grid <= n_sm * min(per_sm, 4)
+        assert slabs >= 1 and slab_cols % 5 == 0 and slabs * slab_cols >= n_cols
+        assert T * slabs <= 32 * grid                               # kMaxOwned tiles per CTA
+        assert 1 <= ret_ctas <= grid and ret_ctas <= (N + 255) // 256
+        assert scratch == T * (slabs * 20 + ret_ctas * 3)
+        n_ok += 1
+    assert n_ok > 300
+    # one step of the bench batch: about one tile per CTA, a fraction of the machine (latency-bound launch)
+    assert L.atc_vecnorm_plan(148, 4, 1, 16384, 4, out) == 0 and int(out[0]) == int(out[1]) == 81
+    # a 1024-step rollout of it: every co-resident CTA, the slab count that balances the tiles
+    assert L.atc_vecnorm_plan(148, 4, 1024, 16384, 4, out) == 0 and int(out[0]) == 592 and (1024 * int(out[1])) % 592 < 592
